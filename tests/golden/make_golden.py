@@ -1,0 +1,273 @@
+#!/usr/bin/env python
+"""Generate the committed golden fixtures by running the REAL reference.
+
+Run in the build container only (needs /root/reference):
+
+    python tests/golden/make_golden.py            # everything (~3 min)
+    python tests/golden/make_golden.py --only epl # one group
+
+Inputs are either tiny and stored in the fixture, or regenerated at test time from
+`sydr_b200.synth` with the seeds recorded here (a SHA-256 of the IQ bytes is stored to
+detect generator drift).  Outputs are what the reference's own functions returned
+(sydr/dsp/acquisition.py, sydr/dsp/tracking.py, sydr/signal/gnsssignal.py,
+sydr/channel/channel_l1ca_borre.py), float64, unmodified.
+"""
+from __future__ import annotations
+
+import argparse
+import hashlib
+import os
+import sys
+import time
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+
+from oracle import ref_import  # noqa: E402
+from sydr_b200 import synth  # noqa: E402
+
+
+def sha(a: np.ndarray) -> str:
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def save(name, **kw):
+    path = os.path.join(HERE, name)
+    np.savez_compressed(path, **kw)
+    print(f"  wrote {name} ({os.path.getsize(path) / 1024:.1f} KiB)")
+
+
+# ----------------------------------------------------------------------------------
+def g_codes(R):
+    codes = np.stack([R.GenerateGPSGoldCode(p) for p in range(1, 33)]).astype(np.int8)
+    spec = {}
+    for fs in (4e6, 10e6, 25e6, 50e6):
+        n = R.getSamplesPerCode(fs)
+        sel = np.unique(np.r_[0:64, np.linspace(0, n - 1, 192).astype(int)])
+        for prn in (1, 19, 32):
+            up = R.UpsampleCode(R.GenerateGPSGoldCode(prn), fs)
+            cf = np.conj(np.fft.fft(up))
+            spec[f"sel_{int(fs)}"] = sel
+            spec[f"spec_{int(fs)}_{prn}"] = cf[sel]
+            spec[f"specabsmax_{int(fs)}_{prn}"] = np.abs(cf).max()
+            spec[f"upsum_{int(fs)}_{prn}"] = np.array([up.sum(), (up * np.arange(n)).sum()])
+    save("codes.npz", codes=codes, **spec)
+
+
+# ----------------------------------------------------------------------------------
+def peak_case_maps():
+    """Deterministic synthetic maps for the second-peak quirks; regenerated at test time
+    (float32-exact values so the fp32 GPU rows see identical numbers)."""
+    rng = np.random.default_rng(77)
+    n, chip, rows = 4000, 4, 5
+    maps = []
+    pos = [0, 1, chip - 1, chip, chip + 1, n - chip - 2, n - chip - 1, n - chip, n - 2, n - 1, 1234]
+    for p in pos:
+        for runner in ("last", "near_lo", "near_hi", "other_row", "random"):
+            m = rng.uniform(0.0, 1.0, (rows, n)).astype(np.float32)
+            r = int(rng.integers(0, rows))
+            m[r, p] = 10.0
+            if runner == "last":
+                m[r, n - 1] = 5.0          # never searched in branches 1 and 3
+            elif runner == "near_lo":
+                m[r, max(0, p - chip)] = 5.0
+            elif runner == "near_hi":
+                m[r, min(n - 1, p + chip)] = 5.0
+            elif runner == "other_row":
+                m[(r + 1) % rows, (p + 100) % n] = 9.0
+            maps.append(m)
+    tie = np.zeros((3, 64), dtype=np.float32)     # equal maxima -> first in C order
+    tie[2, 5] = tie[1, 40] = tie[1, 50] = 7.0
+    tie[1, 10] = 3.0
+    return np.stack(maps), n, chip, tie
+
+
+def g_peaks(R):
+    """TwoCorrelationPeakComparison quirks (acquisition.py:103-111) on synthetic maps."""
+    maps, n, chip, tie = peak_case_maps()
+    out_idx, out_ratio = [], []
+    for m in maps:
+        idx, ratio = R.TwoCorrelationPeakComparison(m.astype(np.float64), n, chip)
+        out_idx.append(idx)
+        out_ratio.append(ratio)
+    tidx, tratio = R.TwoCorrelationPeakComparison(tie.astype(np.float64), 64, 2)
+    save("peaks.npz", idx=np.array(out_idx), ratio=np.array(out_ratio), maps_sha=sha(maps),
+         n=n, chip=chip, tie_idx=np.array(tidx), tie_ratio=tratio)
+
+
+# ----------------------------------------------------------------------------------
+ACQ_CASES = {
+    # name: (fs, nbits, prns_present, seed, doppler_range, doppler_step, coh, noncoh, search_prns, keep_map_prn)
+    "mini4": (4e6, 8, (3, 7), 42, 5000, 250, 2, 3, (3, 7, 9), 3),
+    "cfg1": (4e6, 8, synth.PRNS_8, 1001, 5000, 100, 5, 10, synth.PRNS_8, None),
+    "cfg2": (10e6, 8, synth.PRNS_8, 1002, 5000, 250, 1, 10, tuple(range(1, 33)), 19),
+    "cfg3acq": (25e6, 16, synth.PRNS_12, 1003, 5000, 250, 1, 10, tuple(range(1, 33)), None),
+    "cfg4": (50e6, 8, synth.PRNS_8, 1004, 5000, 50, 1, 20, (3, 5, 31), None),
+}
+
+
+def acq_input(case):
+    fs, nbits, present, seed, dr, ds, coh, noncoh, search, keep = ACQ_CASES[case]
+    n = round(fs * 1e-3)
+    dur = coh * noncoh * 1e-3
+    sc = synth.make_scenario(fs, nbits, dur, present, seed, float(ds))
+    iq = synth.generate_iq(sc)
+    return sc, iq, n
+
+
+def g_acq(R, only=None):
+    for case, (fs, nbits, present, seed, dr, ds, coh, noncoh, search, keep) in ACQ_CASES.items():
+        if only and case not in only:
+            continue
+        t0 = time.time()
+        sc, iq, n = acq_input(case)
+        x = synth.to_complex(iq)[None, :]
+        chip = round(fs / 1.023e6)
+        res = []
+        extra = {}
+        for prn in search:
+            code = R.GenerateGPSGoldCode(prn)
+            cf = np.conj(np.fft.fft(R.UpsampleCode(code, fs)))
+            m = R.PCPS(rfData=x, interFrequency=0.0, samplingFrequency=fs, codeFFT=cf,
+                       dopplerRange=float(dr), dopplerStep=float(ds), samplesPerCode=n,
+                       coherentIntegration=coh, nonCoherentIntegration=noncoh)
+            idx, ratio = R.TwoCorrelationPeakComparison(m, n, chip)
+            rowmax = m.max(axis=1)
+            res.append((prn, idx[0], idx[1], ratio, m[idx[0], idx[1]]))
+            extra[f"rowmax_{prn}"] = rowmax
+            extra[f"rowarg_{prn}"] = m.argmax(axis=1)
+            if keep == prn:
+                extra[f"winrow_{prn}"] = m[idx[0]]
+                if n <= 4000:
+                    extra[f"map_{prn}"] = m.astype(np.float32)
+        res = np.array(res, dtype=np.float64)
+        save(f"acq_{case}.npz", result=res, iq_sha=sha(iq), present=np.array(present),
+             sat_doppler=np.array([s.doppler for s in sc.sats]),
+             sat_delay=np.array([s.delay_chips for s in sc.sats]), **extra)
+        print(f"  acq {case}: {time.time() - t0:.1f}s")
+
+
+# ----------------------------------------------------------------------------------
+def g_epl(R):
+    """Open-loop correlator known answers, incl. awkward NCO states."""
+    out = {}
+    rng = np.random.default_rng(5)
+    for fs, nbits, seed in ((4e6, 8, 11), (10e6, 8, 12), (25e6, 16, 13), (50e6, 16, 14)):
+        sc = synth.make_scenario(fs, nbits, 0.0045, (3, 7), seed, 250.0)
+        iq = synth.generate_iq(sc)
+        x = synth.to_complex(iq)
+        step0 = 1.023e6 / fs
+        cases = []
+        for k in range(6):
+            prn = (3, 7)[k % 2]
+            code = R.GenerateGPSGoldCode(prn)
+            code = np.r_[code[-1], code, code[0]]
+            fc = float(rng.uniform(-5000, 5000)) if k != 5 else 9.548e6 * (fs > 2 * 9.548e6)
+            remc = float(rng.uniform(0, 2 * np.pi))
+            remcode = float(rng.uniform(0, step0)) if k else 0.0
+            step = step0 * (1 + float(rng.uniform(-3e-6, 3e-6)))
+            n = int(np.ceil((1023 - remcode) / step))
+            start = int(rng.integers(0, len(x) - n - 1))
+            sp = [-0.5, 0.0, 0.5] if k != 4 else [-0.25, 0.0, 0.25]
+            r = R.EPL(x[None, start:start + n], code, fs, fc, remc, remcode, step, sp)
+            cases.append([prn, start, n, fc, remc, remcode, step, sp[0], sp[1], sp[2]] + [float(v) for v in r])
+        out[f"fs{int(fs)}"] = np.array(cases)
+        out[f"sha{int(fs)}"] = sha(iq)
+    # the reference's own fixture: 1 ms @ 10 MHz real recording, PRN 2, 3700 Hz
+    # (sydr/unitTest/tracking_in_c.py:22-33).  Values are int8-exact.
+    p = os.path.join(ref_import.REFERENCE_ROOT, "sydr/unitTest/data/i_rfdata.txt")
+    rf = np.loadtxt(p, dtype=np.complex128)
+    assert np.all(rf.real == np.round(rf.real)) and np.abs(rf.real).max() < 128
+    code = R.GenerateGPSGoldCode(2)
+    code = np.r_[code[-1], code, code[0]]
+    r = R.EPL(rf[None, :], code, 10e6, 3700.0, 0.0, 0.0, 1.023e6 / 10e6, [-0.5, 0.0, 0.5])
+    out["unit_iq"] = np.stack([rf.real, rf.imag], axis=1).astype(np.int8).reshape(-1)
+    out["unit_epl"] = np.array(r)
+    # replica KAT of tracking.c:243-247 evaluated through the Python twin
+    t = np.arange(6) / 1e7
+    rep, rem = R.generateReplica(t, 5, -1500.0, 0.0)
+    out["replica"] = rep
+    out["replica_rem"] = rem
+    save("epl.npz", **out)
+
+
+# ----------------------------------------------------------------------------------
+def drive_channel(C, x, fs, prn, ms, acq_cfg, trk_cfg=None):
+    """Drive the live reference ChannelL1CA in-process, one 1 ms tick at a time."""
+    cfg = {"filepath": "none", "sampling_frequency": str(fs), "is_complex": "true",
+           "intermediate_frequency": "0.0", "data_size": "8"}
+    rf = C.RFSignal(cfg)
+    spm = rf.samplesPerMs
+    buf = C.CircularBuffer(int(fs * 1e-3 * 100), np.complex128)
+    chcfg = {
+        "ACQUISITION": acq_cfg,
+        "TRACKING": trk_cfg or {
+            "correlator_early": "-0.5", "correlator_prompt": "0", "correlator_late": "0.5",
+            "dll_damping_ratio": "0.7", "dll_noise_bandwidth": "1.0", "dll_loop_gain": "1.0", "dll_pdi": "0.001",
+            "pll_damping_ratio": "0.7", "pll_noise_bandwidth": "8.0", "pll_loop_gain": "0.25", "pll_pdi": "0.001",
+            "fll_damping_ratio": "0.7", "fll_noise_bandwidth": "15.0", "fll_loop_gain": "1.5", "fll_pdi": "0.001"},
+    }
+    ch = C.ChannelL1CA(0, buf, None, rf, chcfg)
+    ch.setSatellite(prn)
+    acq = None
+    trk = []
+    for tick in range(ms):
+        buf.shift(x[tick * spm:(tick + 1) * spm])
+        res = ch._processHandler()
+        upd = ch.prepareChannelUpdate()
+        for r in res:
+            if r["type"] == C.ChannelMessage.ACQUISITION_UPDATE:
+                acq = (tick, r["frequency_idx"], r["code_idx"], r["peak_ratio"], r["carrierFrequency"],
+                       ch.currentSample)
+            elif r["type"] == C.ChannelMessage.TRACKING_UPDATE:
+                trk.append([tick, r["i_early"], r["q_early"], r["i_prompt"], r["q_prompt"], r["i_late"],
+                            r["q_late"], r["dll"], r["pll"], r["carrier_frequency"], r["code_frequency"],
+                            r["carrier_frequency_error"], r["code_frequency_error"],
+                            upd["unprocessed_samples"], ch.NCO_remainingCode, ch.NCO_remainingCarrier,
+                            ch.track_requiredSamples, ch.currentSample])
+    return acq, np.array(trk)
+
+
+def g_loop(R):
+    C = ref_import.load_channel()
+    out = {}
+    for name, fs, nbits, seed, ms, prns, ds in (("fs4", 4e6, 8, 21, 700, (3, 7), 250),
+                                                ("fs25", 25e6, 16, 23, 260, (11,), 250)):
+        t0 = time.time()
+        sc = synth.make_scenario(fs, nbits, ms * 1e-3, prns, seed, float(ds))
+        iq = synth.generate_iq(sc)
+        x = synth.to_complex(iq)
+        acq_cfg = {"doppler_range": "5000", "doppler_steps": str(ds), "coherent_integration": "1",
+                   "non_coherent_integration": "10", "threshold": "1.5"}
+        for prn in prns:
+            acq, trk = drive_channel(C, x, fs, prn, ms, acq_cfg)
+            out[f"{name}_acq_{prn}"] = np.array(acq, dtype=np.float64)
+            out[f"{name}_trk_{prn}"] = trk
+        out[f"{name}_sha"] = sha(iq)
+        out[f"{name}_meta"] = np.array([fs, nbits, seed, ms, ds], dtype=np.float64)
+        out[f"{name}_prns"] = np.array(prns)
+        print(f"  loop {name}: {time.time() - t0:.1f}s, epochs={len(trk)}")
+    save("loop.npz", **out)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--only", nargs="*", default=None)
+    a = ap.parse_args()
+    R = ref_import.load()
+    groups = {"codes": g_codes, "peaks": g_peaks, "acq": g_acq, "epl": g_epl, "loop": g_loop}
+    for name, fn in groups.items():
+        if a.only and name not in a.only and not (name == "acq" and any(o in ACQ_CASES for o in a.only)):
+            continue
+        print(f"[{name}]")
+        if name == "acq" and a.only and any(o in ACQ_CASES for o in a.only):
+            fn(R, only=a.only)
+        else:
+            fn(R)
+
+
+if __name__ == "__main__":
+    main()
