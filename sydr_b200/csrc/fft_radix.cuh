@@ -1,0 +1,122 @@
+// In-register forward DFT butterflies (radix 2, 3, 4, 5 and Cooley-Tukey composites 8, 10, 16,
+// 20, 25) for the shared-memory mixed-radix FFT of the acquisition kernels.
+//
+// Only *forward* butterflies exist: the inverse transform is run as a forward transform on
+// re/im-swapped data (ifft(z) = swap(fft(swap(z)))/N); the magnitude taken afterwards is
+// invariant under the swap, so the swap back is never materialised.
+#pragma once
+#include <cuda_runtime.h>
+
+namespace sydr {
+
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) {
+    return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+// multiply by -j
+__device__ __forceinline__ float2 mul_mj(float2 a) { return make_float2(a.y, -a.x); }
+
+// exp(-2*pi*i*m/R) for compile-time m (switch tables fold to immediates when unrolled).
+template <int R>
+__device__ __forceinline__ float2 root(int m);
+#include "fft_roots.inc"
+
+template <int R> struct Dft;
+
+template <> struct Dft<1> {
+    __device__ static __forceinline__ void run(float2*) {}
+};
+template <> struct Dft<2> {
+    __device__ static __forceinline__ void run(float2* u) {
+        const float2 a = u[0], b = u[1];
+        u[0] = cadd(a, b);
+        u[1] = csub(a, b);
+    }
+};
+template <> struct Dft<3> {
+    __device__ static __forceinline__ void run(float2* u) {
+        const float s = 0.86602540378443864676f;
+        const float2 t = cadd(u[1], u[2]);
+        const float2 d = csub(u[1], u[2]);
+        const float2 m = make_float2(u[0].x - 0.5f * t.x, u[0].y - 0.5f * t.y);
+        const float2 n = mul_mj(make_float2(s * d.x, s * d.y));
+        u[0] = cadd(u[0], t);
+        u[1] = cadd(m, n);
+        u[2] = csub(m, n);
+    }
+};
+template <> struct Dft<4> {
+    __device__ static __forceinline__ void run(float2* u) {
+        const float2 a = cadd(u[0], u[2]), b = csub(u[0], u[2]);
+        const float2 c = cadd(u[1], u[3]), d = mul_mj(csub(u[1], u[3]));
+        u[0] = cadd(a, c);
+        u[1] = cadd(b, d);
+        u[2] = csub(a, c);
+        u[3] = csub(b, d);
+    }
+};
+template <> struct Dft<5> {
+    __device__ static __forceinline__ void run(float2* u) {
+        const float c1 = 0.30901699437494742410f, c2 = -0.80901699437494742410f;
+        const float s1 = 0.95105651629515357212f, s2 = 0.58778525229247312917f;
+        const float2 t1 = cadd(u[1], u[4]), t2 = cadd(u[2], u[3]);
+        const float2 t3 = csub(u[1], u[4]), t4 = csub(u[2], u[3]);
+        const float2 m1 = make_float2(u[0].x + c1 * t1.x + c2 * t2.x, u[0].y + c1 * t1.y + c2 * t2.y);
+        const float2 m2 = make_float2(u[0].x + c2 * t1.x + c1 * t2.x, u[0].y + c2 * t1.y + c1 * t2.y);
+        const float2 n1 = mul_mj(make_float2(s1 * t3.x + s2 * t4.x, s1 * t3.y + s2 * t4.y));
+        const float2 n2 = mul_mj(make_float2(s2 * t3.x - s1 * t4.x, s2 * t3.y - s1 * t4.y));
+        u[0] = make_float2(u[0].x + t1.x + t2.x, u[0].y + t1.y + t2.y);
+        u[1] = cadd(m1, n1);
+        u[4] = csub(m1, n1);
+        u[2] = cadd(m2, n2);
+        u[3] = csub(m2, n2);
+    }
+};
+
+// Cooley-Tukey composite R = R1*R2:  n = n1*R2 + n2,  k = k1 + R1*k2.
+template <int R1, int R2>
+struct DftCT {
+    static constexpr int R = R1 * R2;
+    __device__ static __forceinline__ void run(float2* u) {
+        float2 t[R];
+#pragma unroll
+        for (int n2 = 0; n2 < R2; ++n2) {
+            float2 a[R1];
+#pragma unroll
+            for (int n1 = 0; n1 < R1; ++n1) a[n1] = u[n1 * R2 + n2];
+            Dft<R1>::run(a);
+#pragma unroll
+            for (int k1 = 0; k1 < R1; ++k1)
+                t[k1 * R2 + n2] = (k1 * n2 == 0) ? a[k1] : cmul(a[k1], root<R>(k1 * n2));
+        }
+#pragma unroll
+        for (int k1 = 0; k1 < R1; ++k1) {
+            float2 b[R2];
+#pragma unroll
+            for (int n2 = 0; n2 < R2; ++n2) b[n2] = t[k1 * R2 + n2];
+            Dft<R2>::run(b);
+#pragma unroll
+            for (int k2 = 0; k2 < R2; ++k2) u[k1 + R1 * k2] = b[k2];
+        }
+    }
+};
+template <> struct Dft<8>  { __device__ static __forceinline__ void run(float2* u) { DftCT<2, 4>::run(u); } };
+template <> struct Dft<10> { __device__ static __forceinline__ void run(float2* u) { DftCT<2, 5>::run(u); } };
+template <> struct Dft<16> { __device__ static __forceinline__ void run(float2* u) { DftCT<4, 4>::run(u); } };
+template <> struct Dft<20> { __device__ static __forceinline__ void run(float2* u) { DftCT<4, 5>::run(u); } };
+template <> struct Dft<25> { __device__ static __forceinline__ void run(float2* u) { DftCT<5, 5>::run(u); } };
+
+// u[r] *= w^r for r = 1..R-1 with log-depth power products (w = base twiddle of this butterfly).
+template <int R>
+__device__ __forceinline__ void twiddle_powers(float2* u, float2 w) {
+    float2 pw[R];
+    pw[0] = make_float2(1.f, 0.f);
+    if (R > 1) pw[1] = w;
+#pragma unroll
+    for (int r = 2; r < R; ++r) pw[r] = cmul(pw[r / 2], pw[r - r / 2]);
+#pragma unroll
+    for (int r = 1; r < R; ++r) u[r] = cmul(u[r], pw[r]);
+}
+
+}  // namespace sydr

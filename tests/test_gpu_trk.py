@@ -1,0 +1,159 @@
+"""K-TRK parity: open-loop correlators against the reference's EPL outputs (1e-4 of the prompt
+magnitude), teacher-forced epochs of the reference channel, and closed-loop trajectories
+(carrier / code frequency within 0.5 Hz, absolute code phase within 1e-3 chip)."""
+import numpy as np
+import pytest
+
+import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+TOL_CORR = 1e-4
+
+
+def corr_err(got, ref):
+    ref = np.asarray(ref, dtype=np.float64)
+    scale = np.hypot(ref[..., 2], ref[..., 3])
+    return np.abs(np.asarray(got) - ref).max(axis=-1) / scale
+
+
+def test_epl_known_answers(golden):
+    from sydr_b200 import _lib as L
+    from sydr_b200.engine import epl_batch, to_device_iq
+    g = golden("epl.npz")
+    for fs, nbits, seed in H.EPL_SETS:
+        iq = H.epl_input(fs, nbits, seed)
+        cases = g[f"fs{int(fs)}"]
+        args = np.zeros(len(cases), dtype=L.EPL_ARGS_DTYPE)
+        args["prn"], args["start"], args["n"] = cases[:, 0], cases[:, 1], cases[:, 2]
+        args["carrier_freq"], args["rem_carrier"] = cases[:, 3], cases[:, 4]
+        args["rem_code"], args["code_step"], args["spacing"] = cases[:, 5], cases[:, 6], cases[:, 7:10]
+        out = epl_batch(to_device_iq(iq), fs, args)
+        e = corr_err(out, cases[:, 10:16])
+        assert e.max() <= TOL_CORR, (fs, e)
+        # same samples as complex64 / complex128 input (the dtype the Python functions receive)
+        from sydr_b200 import synth
+        x = synth.to_complex(iq)
+        for arr in (x.astype(np.complex64), x):
+            out2 = epl_batch(to_device_iq(arr), fs, args)
+            assert corr_err(out2, cases[:, 10:16]).max() <= TOL_CORR
+
+
+def test_epl_function_on_reference_fixture(golden):
+    """EPL() drop-in on the reference's own unit-test recording (PRN 2, 3700 Hz)."""
+    from oracle import sydr_oracle as O
+    from sydr_b200.dsp.tracking import EPL
+    g = golden("epl.npz")
+    u = g["unit_iq"].astype(np.float64)
+    rf = (u[0::2] + 1j * u[1::2])[None, :]
+    out = EPL(rf, O.padded_code(2), 10e6, 3700.0, 0.0, 0.0, 1.023e6 / 10e6, [-0.5, 0.0, 0.5])
+    assert isinstance(out, list) and len(out) == 6 and all(isinstance(v, float) for v in out)
+    assert corr_err(np.array(out), g["unit_epl"]) <= TOL_CORR
+
+
+def reference_epoch_inputs(trk, acq, fs, n_code):
+    """Pre-epoch NCO state of every reference epoch (teacher forcing)."""
+    from oracle import sydr_oracle as O
+    carrier, _, cur = O.acquisition_handoff(int(acq[1]), int(acq[2]), 0.0, 5000.0, 250.0, 0, 10 * n_code,
+                                            int(np.ceil(1023 / (1.023e6 / fs))))
+    n_ep = len(trk)
+    start = np.zeros(n_ep, dtype=np.int64)
+    n = np.zeros(n_ep, dtype=np.int64)
+    fc = np.zeros(n_ep); remc = np.zeros(n_ep); remcode = np.zeros(n_ep); step = np.zeros(n_ep)
+    s_cur, s_n, s_fc, s_remc, s_remcode, s_step = cur, int(np.ceil(1023 / (1.023e6 / fs))), carrier, 0.0, 0.0, 1.023e6 / fs
+    for k in range(n_ep):
+        start[k], n[k], fc[k], remc[k], remcode[k], step[k] = s_cur, s_n, s_fc, s_remc, s_remcode, s_step
+        s_cur += s_n
+        s_fc, s_remcode, s_remc, s_n = trk[k, 9], trk[k, 14], trk[k, 15], int(trk[k, 16])
+        s_step = trk[k, 10] / fs
+    return start, n, fc, remc, remcode, step
+
+
+@pytest.mark.parametrize("name", ["fs4", "fs25"])
+def test_teacher_forced_epochs(golden, name):
+    from sydr_b200 import _lib as L
+    from sydr_b200.engine import epl_batch, to_device_iq
+    g = golden("loop.npz")
+    meta, prns = g[f"{name}_meta"], g[f"{name}_prns"]
+    sc, iq = H.loop_input(meta, prns)
+    fs = float(meta[0])
+    d_iq = to_device_iq(iq)
+    for prn in prns:
+        trk, acq = g[f"{name}_trk_{int(prn)}"], g[f"{name}_acq_{int(prn)}"]
+        start, n, fc, remc, remcode, step = reference_epoch_inputs(trk, acq, fs, round(fs * 1e-3))
+        args = np.zeros(len(trk), dtype=L.EPL_ARGS_DTYPE)
+        args["prn"], args["start"], args["n"] = int(prn), start, n
+        args["carrier_freq"], args["rem_carrier"], args["rem_code"], args["code_step"] = fc, remc, remcode, step
+        args["spacing"] = (-0.5, 0.0, 0.5)
+        out = epl_batch(d_iq, fs, args)
+        e = corr_err(out, trk[:, 1:7])
+        assert e.max() <= TOL_CORR, (name, prn, e.max(), int(e.argmax()))
+
+
+CONFIGS = [dict(cluster=1, threads=0, use_tma=True), dict(cluster=2, threads=0, use_tma=True),
+           dict(cluster=4, threads=128, use_tma=True), dict(cluster=8, threads=0, use_tma=True),
+           dict(cluster=1, threads=256, use_tma=False), dict(cluster=8, threads=64, use_tma=False)]
+
+
+@pytest.mark.parametrize("name", ["fs4", "fs25"])
+@pytest.mark.parametrize("cfg", CONFIGS, ids=lambda c: f"S{c['cluster']}T{c['threads']}{'tma' if c['use_tma'] else 'ldg'}")
+def test_closed_loop_vs_reference_channel(golden, name, cfg):
+    from oracle import sydr_oracle as O
+    from sydr_b200.engine import TrackingEngine, make_trk_states, to_device_iq
+    g = golden("loop.npz")
+    meta, prns = g[f"{name}_meta"], g[f"{name}_prns"]
+    sc, iq = H.loop_input(meta, prns)
+    fs = float(meta[0])
+    n_code = round(fs * 1e-3)
+    chans, refs = [], []
+    for prn in prns:
+        acq = g[f"{name}_acq_{int(prn)}"]
+        carrier, _, cur = O.acquisition_handoff(int(acq[1]), int(acq[2]), 0.0, 5000.0, float(meta[4]), 0, 10 * n_code,
+                                                int(np.ceil(1023 / (1.023e6 / fs))))
+        chans.append(dict(prn=int(prn), carrier_freq=carrier, start_sample=cur, iq_len=len(iq) // 2))
+        refs.append(g[f"{name}_trk_{int(prn)}"])
+    st = make_trk_states(fs, chans)
+    eng = TrackingEngine(fs, st, max_epochs=max(len(r) for r in refs) + 8, **cfg)
+    res = eng.run(to_device_iq(iq))
+    for r, ref in zip(res, refs):
+        n_ep = len(ref)
+        assert len(r) >= n_ep            # the reference stops at its last 1 ms tick, we run to the end of the data
+        r = r[:n_ep]
+        # loop outputs
+        assert np.abs(r["carrier_freq"] - ref[:, 9]).max() <= 0.5
+        assert np.abs(r["code_freq"] - ref[:, 10]).max() <= 0.5
+        # absolute code phase of the *next* epoch: start - remCode/codeStep, in chips
+        step = ref[:, 10] / fs
+        n_ref = np.r_[r["n"][0], ref[:-1, 16]]                       # reference epoch lengths
+        ref_end = r["start"][0] + np.cumsum(n_ref)                   # reference epoch end samples
+        ref_abs = ref_end - ref[:, 14] / step
+        ours_abs = (r["start"] + r["n"]) - r["rem_code"] / (r["code_freq"] / fs)
+        assert np.abs(ours_abs - ref_abs).max() * (1.023e6 / fs) <= 1e-3, np.abs(ours_abs - ref_abs).max()
+        # correlators (closed loop, so compared loosely: 1 % of prompt magnitude outside arctan wraps)
+        e = corr_err(r["corr"], ref[:, 1:7])
+        assert np.median(e) <= 1e-3
+
+
+def test_bit_identical_across_launch_splits(golden):
+    """Stopping after k epochs and resuming gives the same trajectory as one launch (state round trip)."""
+    from oracle import sydr_oracle as O
+    from sydr_b200.engine import TrackingEngine, make_trk_states, to_device_iq
+    g = golden("loop.npz")
+    meta, prns = g["fs4_meta"], g["fs4_prns"]
+    sc, iq = H.loop_input(meta, prns)
+    fs = float(meta[0])
+    chans = []
+    for prn in prns:
+        acq = g[f"fs4_acq_{int(prn)}"]
+        carrier, _, cur = O.acquisition_handoff(int(acq[1]), int(acq[2]), 0.0, 5000.0, 250.0, 0, 40000, 4000)
+        chans.append(dict(prn=int(prn), carrier_freq=carrier, start_sample=cur, iq_len=len(iq) // 2))
+    d_iq = to_device_iq(iq)
+    one = TrackingEngine(fs, make_trk_states(fs, chans), max_epochs=700, cluster=2).run(d_iq)
+    eng = TrackingEngine(fs, make_trk_states(fs, chans), max_epochs=100, cluster=2)
+    pieces = [[] for _ in chans]
+    for _ in range(8):
+        for c, r in enumerate(eng.run(d_iq)):
+            pieces[c].append(r)
+    for c in range(len(chans)):
+        joined = np.concatenate(pieces[c])
+        assert joined.tobytes() == one[c][:len(joined)].tobytes() and len(joined) == len(one[c])
