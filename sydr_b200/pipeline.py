@@ -1,0 +1,93 @@
+"""Cold-start pipeline on one GPU: 32-PRN PCPS acquisition -> hand-off -> batched closed-loop
+tracking of the acquired channels over a recording (the BASELINE.json headline workload).
+
+This is the public call a user makes for whole-recording processing; it replaces the
+receiver's per-millisecond loop over per-channel processes
+(sydr/receiver/receiver.py:120-139, sydr/channel/channelManager.py:149-188) by two batched
+GPU dispatches with the reference's scalar hand-off (channel_l1ca_borre.py:301-316) between
+them.
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+import torch
+
+from . import _lib as L
+from .engine import (CODE_CHIPS, CODE_FREQ, IQ_PAD_BYTES, AcquisitionEngine, TrackingEngine, make_trk_states,
+                     n_complex_samples)
+
+
+class ColdStartPipeline:
+    def __init__(self, fs, nbits, search_prns, n_channels, doppler_range=5000.0, doppler_step=250.0, coh=1,
+                 noncoh=10, max_seconds=2.0, inter_freq=0.0, threshold=1.5, channel_cfg=None, device=None,
+                 cluster=0, threads=0, use_tma=True):
+        L.require_device()
+        if device is not None:
+            torch.cuda.set_device(device)
+        self.device = torch.device("cuda", torch.cuda.current_device())
+        self.fs, self.nbits, self.inter_freq = float(fs), int(nbits), float(inter_freq)
+        self.n_channels, self.threshold = int(n_channels), float(threshold)
+        self.channel_cfg = channel_cfg
+        self.trk_cfg = dict(cluster=cluster, threads=threads, use_tma=use_tma)
+        self.acq = AcquisitionEngine(fs, inter_freq, doppler_range, doppler_step, coh, noncoh, list(search_prns),
+                                     device=self.device)
+        self.max_samples = int(round(max_seconds * fs))
+        self.max_epochs = int(math.ceil(max_seconds * 1000.0)) + 8
+        self._tdt = torch.int8 if nbits == 8 else torch.int16
+        pad = IQ_PAD_BYTES // (1 if nbits == 8 else 2)
+        self._d_iq = torch.zeros(2 * self.max_samples + pad, dtype=self._tdt, device=self.device)
+        self._trk = None
+        self.stream = torch.cuda.current_stream()
+
+    def close(self):
+        self.acq.close()
+
+    # ---- stages --------------------------------------------------------------------------
+    def device_buffer(self, n_samples: int) -> torch.Tensor:
+        return self._d_iq[:2 * n_samples]
+
+    def upload(self, host_iq: torch.Tensor) -> torch.Tensor:
+        """Pinned host interleaved IQ -> device (async on the current stream)."""
+        n = host_iq.numel()
+        if n > 2 * self.max_samples:
+            raise L.SydrError("recording chunk longer than max_seconds")
+        d = self._d_iq[:n]
+        d.copy_(host_iq, non_blocking=True)
+        return d
+
+    def select_channels(self, peaks: np.ndarray):
+        """PRNs whose metric exceeds the threshold, best first, at most n_channels."""
+        order = np.argsort(-peaks["ratio"], kind="stable")
+        sel = [i for i in order if peaks["ratio"][i] > self.threshold][:self.n_channels]
+        return sorted(sel, key=lambda i: int(peaks["prn"][i]))
+
+    def process_device(self, d_iq: torch.Tensor) -> dict:
+        """Acquisition + hand-off + tracking on IQ already resident in HBM."""
+        n = n_complex_samples(d_iq)
+        self.acq.launch(d_iq)
+        peaks = self.acq.fetch()["peaks"]                       # 24 B per PRN, D2H
+        sel = self.select_channels(peaks)
+        chans = []
+        for i in sel:
+            carrier, _, cur = self.acq.handoff(peaks[i])
+            chans.append(dict(prn=int(peaks["prn"][i]), carrier_freq=carrier, start_sample=cur, iq_len=n))
+        states = make_trk_states(self.fs, chans, self.channel_cfg)
+        if self._trk is None or self._trk.n_ch != len(chans):
+            self._trk = TrackingEngine(self.fs, states, self.max_epochs, device=self.device, **self.trk_cfg)
+        else:
+            self._trk._states.copy_(torch.from_numpy(states.view(np.uint8).reshape(-1)), non_blocking=False)
+        self._trk.launch(d_iq)
+        return dict(peaks=peaks, channels=chans)
+
+    def collect(self) -> list:
+        """D2H of the per-epoch tracking records of the last process_device()."""
+        return self._trk.fetch()
+
+    def process_host(self, host_iq: torch.Tensor) -> dict:
+        """End to end: pinned host IQ in, acquisition table + per-epoch tracking records out."""
+        d = self.upload(host_iq)
+        out = self.process_device(d)
+        out["epochs"] = self.collect()
+        return out
