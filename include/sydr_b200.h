@@ -187,6 +187,11 @@ int sydr_trk_run(const void* d_iq, int iq_dtype, long long iq_alloc_samples, dou
                  sydr_trk_epoch* d_out, int max_epochs, int* d_nepochs,
                  const sydr_trk_config* cfg, void* stream);
 
+/* Diagnostics: per-phase clock64 counters of the loop-closing thread, d_buf = n_channels*8
+ * int64 on the device ([0..6] = constants+TMA issue, barrier, window wait, correlate, block
+ * reduction, cluster gather, loop closure; [7] = epochs).  NULL switches it off. */
+int sydr_trk_profile_buffer(long long* d_buf);
+
 /* Host helper: initial state exactly as ChannelL1CA leaves it after acquisition
  * (channel_l1ca_borre.py:110-120, 250-251, 301-311). */
 int sydr_trk_state_init(sydr_trk_state* h_state, int prn, double fs, double carrier_freq,

@@ -301,6 +301,7 @@ struct TrkParams {
     int max_epochs;
     int Q;                   // chunks per CTA per epoch (window = Q*C samples)
     int use_tma;
+    long long* prof;         // optional [n_channels][8] phase cycle counters of thread 0 (NULL = off)
 };
 
 struct EpochCtl {            // published by the loop thread each epoch
@@ -381,6 +382,16 @@ __global__ void __launch_bounds__(kTrkMaxThreads) trk_borre_kernel(const TrkPara
 
     int epoch = 0;
     int status = 0;
+    long long pc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long tprev = 0;
+    const bool prof = (P.prof != nullptr) && tid == 0;
+#define SYDR_TICK(k)                                   \
+    if (prof) {                                        \
+        const long long now__ = clock64();             \
+        pc[k] += now__ - tprev;                        \
+        tprev = now__;                                 \
+    }
+    if (prof) tprev = clock64();
     while (true) {
         const int buf = epoch & 1;
         if (tid == 0) {
@@ -398,8 +409,10 @@ __global__ void __launch_bounds__(kTrkMaxThreads) trk_borre_kernel(const TrkPara
                 }
             }
         }
+        SYDR_TICK(0)                                   // epoch constants + TMA issue
         __syncthreads();
         if (ctl.stop) break;
+        SYDR_TICK(1)                                   // barrier
 
         // ---- correlate this CTA's window
         const long long a = ctl.a;
@@ -409,6 +422,7 @@ __global__ void __launch_bounds__(kTrkMaxThreads) trk_borre_kernel(const TrkPara
         float acc[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         int err = 0;
         if (P.use_tma) mbar_wait(&bar_data[buf], (epoch >> 1) & 1);
+        SYDR_TICK(2)                                   // wait for the staged window
         for (int q = tid; q < Q; q += blockDim.x) {
             const int j0 = (int)(wstart + (long long)q * C) - lead;
             if (j0 >= ctl.ec.n) break;
@@ -420,9 +434,11 @@ __global__ void __launch_bounds__(kTrkMaxThreads) trk_borre_kernel(const TrkPara
             }
             correlate_chunk<DT>(src, j0, ctl.ec, cb, acc, err);
         }
+        SYDR_TICK(3)                                   // correlate (thread 0's chunks)
         acc[6] = err ? 1.f : 0.f;                     // code-index overflow anywhere aborts the channel
         float part[7];
         block_sum<7>(acc, red, part);
+        SYDR_TICK(4)                                   // block reduction (waits for the slowest warp)
 
         // ---- gather the cluster's partial sums and close the loops (warp 0)
         if (tid < 32) {
@@ -451,12 +467,14 @@ __global__ void __launch_bounds__(kTrkMaxThreads) trk_borre_kernel(const TrkPara
 #pragma unroll
                 for (int k = 0; k < 6; ++k) c[k] = (double)part[k];
             }
+            SYDR_TICK(5)                               // cluster all-gather
             if (tid == 0) {
                 sydr_trk_epoch rec;
                 close_loops(st, cfgs, P.fs, c, rec);
                 if (part[6] != 0.f) status = SYDR_ERR_STATE;
                 if (rank == 0) P.out[(long long)ch * P.max_epochs + epoch] = rec;
             }
+            SYDR_TICK(6)                               // loop closure + record store
         }
         ++epoch;
         // (the __syncthreads at the top of the next iteration orders ctl/window reuse)
@@ -465,6 +483,10 @@ __global__ void __launch_bounds__(kTrkMaxThreads) trk_borre_kernel(const TrkPara
     // the window of the epoch that will not run was already requested: drain it before exit
     if (P.use_tma && epoch > 0) mbar_wait(&bar_data[epoch & 1], (epoch >> 1) & 1);
 
+    if (prof && rank == 0) {
+        for (int k = 0; k < 7; ++k) P.prof[ch * 8 + k] = pc[k];
+        P.prof[ch * 8 + 7] = epoch;
+    }
     if (tid == 0 && rank == 0) {
         gst->cur = st.cur; gst->n_req = st.n_req; gst->epochs_done = st.epochs_done;
         gst->carrier_freq = st.carrier_freq; gst->code_freq = st.code_freq; gst->code_step = st.code_step;
@@ -520,7 +542,16 @@ int launch_trk(const TrkParams& P, int n_channels, int cluster, int threads, cud
 
 }  // namespace
 
+static long long* g_trk_prof = nullptr;    // set by sydr_trk_profile_buffer (diagnostics)
+
 extern "C" {
+
+// Diagnostics: give the tracking kernel a device buffer of n_channels*8 int64 to fill with
+// per-phase cycle counts of the loop-closing thread (NULL switches it off).
+int sydr_trk_profile_buffer(long long* d_buf) {
+    g_trk_prof = d_buf;
+    return SYDR_OK;
+}
 
 int sydr_epl_batch(const void* d_iq, int iq_dtype, long long iq_len, double fs, const sydr_epl_args* d_args,
                    int n_calls, double* d_out, void* stream) {
@@ -599,6 +630,7 @@ int sydr_trk_run(const void* d_iq, int iq_dtype, long long iq_alloc_samples, dou
     P.max_epochs = max_epochs;
     P.Q = Q;
     P.use_tma = use_tma;
+    P.prof = g_trk_prof;
     cudaStream_t s = (cudaStream_t)stream;
     switch (iq_dtype) {
         case SYDR_IQ_I8: return launch_trk<SYDR_IQ_I8>(P, n_channels, cluster, threads, s);
