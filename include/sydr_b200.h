@@ -50,6 +50,8 @@ int         sydr_device_count(void);            /* 0 when no CUDA device is usab
 int         sydr_set_device(int device);
 /* Measured FP32 FMA-chain peak of the current device (roofline denominator). */
 int         sydr_measure_fp32_peak(double* h_tflops, double* h_sm_clock_mhz);
+/* Measured FP64 FMA throughput and dependent-FMA latencies (cycles) of the current device. */
+int         sydr_measure_fp64_peak(double* h_tflops, double* h_dfma_latency_cycles, double* h_ffma_latency_cycles);
 /* Kernel-launch counter (all kernels launched by this library since load / reset). */
 long long   sydr_launch_count(void);
 void        sydr_reset_launch_count(void);

@@ -93,6 +93,7 @@ SIGNATURES = {
     "sydr_device_count": (_i, []),
     "sydr_set_device": (_i, [_i]),
     "sydr_measure_fp32_peak": (_i, [_dp, _dp]),
+    "sydr_measure_fp64_peak": (_i, [_dp, _dp, _dp]),
     "sydr_launch_count": (_ll, []),
     "sydr_reset_launch_count": (None, []),
     "sydr_ca_code": (_i, [_i, _vp]),

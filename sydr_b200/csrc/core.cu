@@ -114,6 +114,30 @@ __global__ void __launch_bounds__(256) fp32_peak_kernel(float* sink, int iters, 
     if (s == 123.456f) sink[0] = s;
 }
 
+__global__ void __launch_bounds__(256) fp64_peak_kernel(double* sink, int iters, double a, double b) {
+    double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+            x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+        }
+    }
+    const double s = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+    if (s == 123.456) sink[0] = s;
+}
+// dependent-chain latency probes (one warp)
+__global__ void latency_kernel(long long* out, int iters, double a, double b, float fa, float fb) {
+    double x = threadIdx.x;
+    long long t0 = clock64();
+    for (int i = 0; i < iters; ++i) x = fma(x, a, b);
+    long long t1 = clock64();
+    float y = threadIdx.x;
+    for (int i = 0; i < iters; ++i) y = fmaf(y, fa, fb);
+    long long t2 = clock64();
+    if (threadIdx.x == 0) { out[0] = t1 - t0; out[1] = t2 - t1; out[2] = (long long)(x + y); }
+}
+
 }  // namespace sydr
 
 using namespace sydr;
@@ -169,6 +193,42 @@ int sydr_measure_fp32_peak(double* h_tflops, double* h_sm_clock_mhz) {
     cudaFree(sink);
     *h_tflops = best;
     if (h_sm_clock_mhz) *h_sm_clock_mhz = clk / 1000.0;
+    return SYDR_OK;
+}
+
+int sydr_measure_fp64_peak(double* h_tflops, double* h_dfma_latency_cycles, double* h_ffma_latency_cycles) {
+    SYDR_REQUIRE(h_tflops != nullptr, SYDR_ERR_ARG, "h_tflops is NULL");
+    int dev = 0, sms = 0;
+    SYDR_CUDA_CHECK(cudaGetDevice(&dev));
+    SYDR_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    double* sink = nullptr;
+    SYDR_CUDA_CHECK(cudaMalloc(&sink, 64));
+    cudaEvent_t e0, e1;
+    SYDR_CUDA_CHECK(cudaEventCreate(&e0));
+    SYDR_CUDA_CHECK(cudaEventCreate(&e1));
+    const int iters = 512, grid = sms * 8;
+    double best = 0.0;
+    for (int rep = 0; rep < 4; ++rep) {
+        SYDR_CUDA_CHECK(cudaEventRecord(e0));
+        fp64_peak_kernel<<<grid, 256>>>(sink, iters, 1.0000001, 1e-9);
+        count_launch();
+        SYDR_CUDA_CHECK(cudaEventRecord(e1));
+        SYDR_CUDA_CHECK(cudaEventSynchronize(e1));
+        float ms = 0;
+        SYDR_CUDA_CHECK(cudaEventElapsedTime(&ms, e0, e1));
+        const double tf = 2.0 * 64.0 * iters * 256.0 * grid / (ms * 1e-3) / 1e12;
+        if (rep > 0 && tf > best) best = tf;
+    }
+    *h_tflops = best;
+    long long h[3] = {0, 0, 0};
+    latency_kernel<<<1, 32>>>(reinterpret_cast<long long*>(sink), 4096, 1.0000001, 1e-9, 1.0000001f, 1e-9f);
+    count_launch();
+    SYDR_CUDA_CHECK(cudaMemcpy(h, sink, sizeof(h), cudaMemcpyDeviceToHost));
+    if (h_dfma_latency_cycles) *h_dfma_latency_cycles = h[0] / 4096.0;
+    if (h_ffma_latency_cycles) *h_ffma_latency_cycles = h[1] / 4096.0;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(sink);
     return SYDR_OK;
 }
 
