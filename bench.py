@@ -255,7 +255,7 @@ def main():
         chans = [dict(prn=int(peaks["prn"][i]), carrier_freq=pipe.acq.handoff(peaks[i])[0],
                       start_sample=pipe.acq.handoff(peaks[i])[2], iq_len=chunk_samples) for i in sel]
         st = make_trk_states(FS, chans)
-        pipe._trk._states.copy_(torch.from_numpy(st.view(np.uint8).reshape(-1)))
+        pipe._trk.reset(st)
         t0 = torch.cuda.Event(enable_timing=True)
         t0.record()
         pipe._trk.launch(d_iq)

@@ -176,7 +176,11 @@ typedef struct {
     int32_t cluster;
     int32_t threads;
     int32_t use_tma;        /* 1 = cp.async.bulk staged smem windows (default), 0 = LDG     */
-    int32_t reserved;
+    int32_t append;         /* 1 = records go to d_out[ch][state.epochs_done ...] so that
+                               successive calls on a growing recording fill one array;
+                               d_nepochs then reports the cumulative count                  */
+    int64_t iq_len;         /* > 0: valid samples per recording for this call (overrides
+                               the states' iq_len; streaming upload)                       */
 } sydr_trk_config;
 
 /* Closed-loop Borre tracking (runTracking, channel_l1ca_borre.py:333-451: EPL +

@@ -56,7 +56,8 @@ class TrkEpoch(C.Structure):
 
 
 class TrkConfig(C.Structure):
-    _fields_ = [("cluster", C.c_int32), ("threads", C.c_int32), ("use_tma", C.c_int32), ("reserved", C.c_int32)]
+    _fields_ = [("cluster", C.c_int32), ("threads", C.c_int32), ("use_tma", C.c_int32), ("append", C.c_int32),
+                ("iq_len", C.c_int64)]
 
 
 # numpy views of the same layouts (device buffers are torch uint8 tensors reinterpreted)

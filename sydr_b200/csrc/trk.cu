@@ -378,6 +378,8 @@ struct TrkParams {
     int max_epochs;
     int Q;                   // chunks per CTA per epoch (window = Q*C samples)
     int use_tma;
+    int append;              // records are indexed by the cumulative epoch count
+    long long iq_len;        // > 0: overrides the states' iq_len
     long long* prof;         // optional [n_channels][8] phase cycle counters of thread 0 (NULL = off)
 };
 
@@ -402,6 +404,7 @@ struct TrkShared {           // static shared memory of the closed-loop kernel
     CarrierState sk;         // owned by warp 1
     LoopConst K;
     int n_hist[2];           // samples of epoch e (index e & 1), for the carrier warp
+    int rec_base;            // index of this call's first record in the channel's output row
     int status;
     long long pc[8];         // diagnostics
     long long tprev;
@@ -493,7 +496,7 @@ __device__ __noinline__ void trk_code_warp(TrkShared& sh, const TrkParams& P, ui
         st.nco_code = nco_code;
         if (errflag != 0.0) status = SYDR_ERR_STATE;
         if (rank == 0) {
-            double* rec = reinterpret_cast<double*>(P.out + (long long)ch * P.max_epochs + e);
+            double* rec = reinterpret_cast<double*>(P.out + (long long)ch * P.max_epochs + sh.rec_base + e);
             if (lane < 6) rec[lane] = ck;              // i_early .. q_late
             else if (lane == 6) rec[6] = nco_code;
             else if (lane == 9) rec[9] = st.code_freq;
@@ -507,7 +510,7 @@ __device__ __noinline__ void trk_code_warp(TrkShared& sh, const TrkParams& P, ui
     }
     // ---- publish epoch `epoch`
     if (st.n_req <= 0 || (long long)st.n_req + SPV > (long long)S * P.Q * C) status = SYDR_ERR_STATE;
-    const bool stop = (status != 0) || (epoch >= P.max_epochs) || (st.cur + st.n_req > sh.cfgs.iq_len);
+    const bool stop = (status != 0) || (sh.rec_base + epoch >= P.max_epochs) || (st.cur + st.n_req > sh.cfgs.iq_len);
     if (!stop) {
         double t_start, t_step, t_inv;
         tap_const(st.rem_code, sh.cfgs.spacing[min(lane, 2)], st.code_step, st.n_req, t_start, t_step, t_inv);
@@ -569,7 +572,7 @@ __device__ __noinline__ void trk_carrier_warp(TrkShared& sh, const TrkParams& P,
         st.nco_carrier_err = ph_err;
         st.nco_carrier = nco_car;
         if (rank == 0) {
-            double* rec = reinterpret_cast<double*>(P.out + (long long)ch * P.max_epochs + e);
+            double* rec = reinterpret_cast<double*>(P.out + (long long)ch * P.max_epochs + sh.rec_base + e);
             if (lane == 7) rec[7] = nco_car;
             else if (lane == 8) rec[8] = st.carrier_freq;
             else if (lane == 11) rec[11] = ph_err;
@@ -608,6 +611,8 @@ __global__ void __launch_bounds__(kTrkMaxThreads) trk_borre_kernel(const TrkPara
     sydr_trk_state* gst = P.states + ch;
     if (tid == 0) {
         sh.cfgs = *gst;
+        if (P.iq_len > 0) sh.cfgs.iq_len = P.iq_len;
+        sh.rec_base = P.append ? (int)sh.cfgs.epochs_done : 0;
         const sydr_trk_state& g = sh.cfgs;
         sh.sc.cur = g.cur; sh.sc.n_req = (int)g.n_req;
         sh.sc.code_freq = g.code_freq; sh.sc.code_step = g.code_step; sh.sc.rem_code = g.rem_code;
@@ -697,7 +702,7 @@ __global__ void __launch_bounds__(kTrkMaxThreads) trk_borre_kernel(const TrkPara
         gst->nco_code = sh.sc.nco_code; gst->nco_code_err = sh.sc.nco_code_err;
         gst->nco_carrier = sh.sk.nco_carrier; gst->nco_carrier_err = sh.sk.nco_carrier_err;
         gst->status = sh.status;
-        P.nepochs[ch] = epoch;
+        P.nepochs[ch] = sh.rec_base + epoch;
     }
     if (S > 1) cluster_sync_all();                  // nobody leaves while peers may still write here
 }
@@ -833,6 +838,8 @@ int sydr_trk_run(const void* d_iq, int iq_dtype, long long iq_alloc_samples, dou
     P.max_epochs = max_epochs;
     P.Q = Q;
     P.use_tma = use_tma;
+    P.append = cfg ? (cfg->append != 0) : 0;
+    P.iq_len = cfg ? cfg->iq_len : 0;
     P.prof = g_trk_prof;
     cudaStream_t s = (cudaStream_t)stream;
     switch (iq_dtype) {

@@ -208,7 +208,7 @@ class TrackingEngine:
         self.fs = float(fs)
         self.n_ch = len(states)
         self.max_epochs = int(max_epochs)
-        self.cfg = L.TrkConfig(int(cluster), int(threads), 1 if use_tma else 0, 0)
+        self.cfg = L.TrkConfig(int(cluster), int(threads), 1 if use_tma else 0, 0, 0)
         st = np.ascontiguousarray(states)
         assert st.dtype == L.TRK_STATE_DTYPE
         self._states = torch.from_numpy(st.view(np.uint8).reshape(-1).copy()).to(self.device)
@@ -221,8 +221,18 @@ class TrackingEngine:
         st["iq_len"] = iq_len
         self._states.copy_(torch.from_numpy(st.view(np.uint8).reshape(-1)))
 
-    def launch(self, iq_dev: torch.Tensor, stream=None):
+    def reset(self, states: np.ndarray):
+        """Load fresh channel states (same channel count) without reallocating."""
+        st = np.ascontiguousarray(states)
+        assert st.dtype == L.TRK_STATE_DTYPE and len(st) == self.n_ch
+        self._states.copy_(torch.from_numpy(st.view(np.uint8).reshape(-1)))
+
+    def launch(self, iq_dev: torch.Tensor, stream=None, iq_len: int = 0, append: bool = False):
+        """Enqueue one tracking launch.  iq_len > 0 limits every recording to its first iq_len
+        samples (streaming upload); append=True continues the record arrays of earlier launches."""
         iq_dev = ensure_padded(iq_dev)
+        self.cfg.iq_len = int(iq_len)
+        self.cfg.append = 1 if append else 0
         store_bytes = iq_dev.untyped_storage().nbytes() - iq_dev.storage_offset() * iq_dev.element_size()
         code = iq_code(iq_dev)
         alloc_samples = store_bytes // _IQ_BYTES[code]

@@ -39,7 +39,7 @@ class ColdStartPipeline:
         pad = IQ_PAD_BYTES // (1 if nbits == 8 else 2)
         self._d_iq = torch.zeros(2 * self.max_samples + pad, dtype=self._tdt, device=self.device)
         self._trk = None
-        self.stream = torch.cuda.current_stream()
+        self._copy_stream = torch.cuda.Stream(device=self.device)
 
     def close(self):
         self.acq.close()
@@ -63,31 +63,66 @@ class ColdStartPipeline:
         sel = [i for i in order if peaks["ratio"][i] > self.threshold][:self.n_channels]
         return sorted(sel, key=lambda i: int(peaks["prn"][i]))
 
+    def _start_tracking(self, peaks: np.ndarray, n_samples: int):
+        """Scalar hand-off (channel_l1ca_borre.py:301-316) and fresh channel states on the device."""
+        sel = self.select_channels(peaks)
+        chans = []
+        for i in sel:
+            carrier, _, cur = self.acq.handoff(peaks[i])
+            chans.append(dict(prn=int(peaks["prn"][i]), carrier_freq=carrier, start_sample=cur, iq_len=n_samples))
+        states = make_trk_states(self.fs, chans, self.channel_cfg)
+        if self._trk is None or self._trk.n_ch != len(chans):
+            self._trk = TrackingEngine(self.fs, states, self.max_epochs, device=self.device, **self.trk_cfg)
+        else:
+            self._trk.reset(states)
+        return chans
+
     def process_device(self, d_iq: torch.Tensor) -> dict:
         """Acquisition + hand-off + tracking on IQ already resident in HBM."""
         n = n_complex_samples(d_iq)
         self.acq.launch(d_iq)
         peaks = self.acq.fetch()["peaks"]                       # 24 B per PRN, D2H
-        sel = self.select_channels(peaks)
-        chans = []
-        for i in sel:
-            carrier, _, cur = self.acq.handoff(peaks[i])
-            chans.append(dict(prn=int(peaks["prn"][i]), carrier_freq=carrier, start_sample=cur, iq_len=n))
-        states = make_trk_states(self.fs, chans, self.channel_cfg)
-        if self._trk is None or self._trk.n_ch != len(chans):
-            self._trk = TrackingEngine(self.fs, states, self.max_epochs, device=self.device, **self.trk_cfg)
-        else:
-            self._trk._states.copy_(torch.from_numpy(states.view(np.uint8).reshape(-1)), non_blocking=False)
+        chans = self._start_tracking(peaks, n)
         self._trk.launch(d_iq)
         return dict(peaks=peaks, channels=chans)
 
     def collect(self) -> list:
-        """D2H of the per-epoch tracking records of the last process_device()."""
+        """D2H of the per-epoch tracking records of the last process_*()."""
         return self._trk.fetch()
 
-    def process_host(self, host_iq: torch.Tensor) -> dict:
-        """End to end: pinned host IQ in, acquisition table + per-epoch tracking records out."""
-        d = self.upload(host_iq)
-        out = self.process_device(d)
+    def process_host(self, host_iq: torch.Tensor, pieces: int = 8) -> dict:
+        """End to end: pinned host IQ in, acquisition table + per-epoch tracking records out.
+        The upload is cut into `pieces` segments on a copy stream; acquisition starts as soon as
+        the dwell has landed and tracking follows the upload piece by piece (state carried on
+        the device, records appended), so H2D and compute overlap."""
+        n_el = host_iq.numel()
+        n = n_el // 2
+        if n > self.max_samples:
+            raise L.SydrError("recording chunk longer than max_seconds")
+        comp = torch.cuda.current_stream()
+        first = min(n, self.acq.required_samples + 4 * self.acq.n_code)
+        step = max(1, -(-(n - first) // max(1, pieces)))
+        bounds = [first]
+        while bounds[-1] < n:
+            bounds.append(min(n, bounds[-1] + step))
+        d = self._d_iq[:n_el]
+        events = []
+        self._copy_stream.wait_stream(comp)                      # earlier kernels are done with the buffer
+        with torch.cuda.stream(self._copy_stream):
+            lo = 0
+            for hi in bounds:
+                d[2 * lo:2 * hi].copy_(host_iq[2 * lo:2 * hi], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(self._copy_stream)
+                events.append(ev)
+                lo = hi
+        comp.wait_event(events[0])
+        self.acq.launch(d[:2 * first])
+        peaks = self.acq.fetch()["peaks"]
+        chans = self._start_tracking(peaks, n)
+        for hi, ev in zip(bounds, events):
+            comp.wait_event(ev)
+            self._trk.launch(d, iq_len=hi, append=True)
+        out = dict(peaks=peaks, channels=chans)
         out["epochs"] = self.collect()
         return out

@@ -157,3 +157,25 @@ def test_bit_identical_across_launch_splits(golden):
     for c in range(len(chans)):
         joined = np.concatenate(pieces[c])
         assert joined.tobytes() == one[c][:len(joined)].tobytes() and len(joined) == len(one[c])
+
+
+def test_streaming_append_matches_single_launch(golden):
+    """Tracking a recording that arrives in pieces (iq_len raised launch by launch, records appended)
+    is bit-identical to one launch over the whole recording."""
+    from oracle import sydr_oracle as O
+    from sydr_b200.engine import TrackingEngine, make_trk_states, to_device_iq
+    g = golden("loop.npz")
+    meta, prns = g["fs25_meta"], g["fs25_prns"]
+    sc, iq = H.loop_input(meta, prns)
+    fs = float(meta[0])
+    n = len(iq) // 2
+    acq = g[f"fs25_acq_{int(prns[0])}"]
+    carrier, _, cur = O.acquisition_handoff(int(acq[1]), int(acq[2]), 0.0, 5000.0, 250.0, 0, 250000, 25000)
+    chans = [dict(prn=int(prns[0]), carrier_freq=carrier, start_sample=cur, iq_len=n)]
+    d_iq = to_device_iq(iq)
+    one = TrackingEngine(fs, make_trk_states(fs, chans), max_epochs=300, cluster=8).run(d_iq)[0]
+    eng = TrackingEngine(fs, make_trk_states(fs, chans), max_epochs=300, cluster=8)
+    for frac in (0.2, 0.21, 0.5, 0.77, 1.0):
+        eng.launch(d_iq, iq_len=int(n * frac), append=True)
+    parts = eng.fetch()[0]
+    assert len(parts) == len(one) and parts.tobytes() == one.tobytes()
