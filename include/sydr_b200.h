@@ -181,6 +181,9 @@ typedef struct {
                                d_nepochs then reports the cumulative count                  */
     int64_t iq_len;         /* > 0: valid samples per recording for this call (overrides
                                the states' iq_len; streaming upload)                       */
+    double  min_tap_gap;    /* smallest distance, in chips, between the chip-boundary positions
+                               of two correlators (0 = 0.5, the -0.5/0/+0.5 spacing); sizes
+                               the per-thread chunk for the split-sum path                  */
 } sydr_trk_config;
 
 /* Closed-loop Borre tracking (runTracking, channel_l1ca_borre.py:333-451: EPL +
@@ -193,9 +196,9 @@ int sydr_trk_run(const void* d_iq, int iq_dtype, long long iq_alloc_samples, dou
                  sydr_trk_epoch* d_out, int max_epochs, int* d_nepochs,
                  const sydr_trk_config* cfg, void* stream);
 
-/* Diagnostics: per-phase clock64 counters of the loop-closing thread, d_buf = n_channels*8
- * int64 on the device ([0..6] = constants+TMA issue, barrier, window wait, correlate, block
- * reduction, cluster gather, loop closure; [7] = epochs).  NULL switches it off. */
+/* Diagnostics: per-phase clock64 counters of the loop-closing thread, d_buf = n_channels*16
+ * int64 on the device ([0..7] = epoch constants, barrier, window wait, correlate, warp
+ * reduction + send, gather wait, loop closure, gather totals; [15] = epochs).  NULL = off. */
 int sydr_trk_profile_buffer(long long* d_buf);
 
 /* Host helper: initial state exactly as ChannelL1CA leaves it after acquisition

@@ -57,7 +57,7 @@ class TrkEpoch(C.Structure):
 
 class TrkConfig(C.Structure):
     _fields_ = [("cluster", C.c_int32), ("threads", C.c_int32), ("use_tma", C.c_int32), ("append", C.c_int32),
-                ("iq_len", C.c_int64)]
+                ("iq_len", C.c_int64), ("min_tap_gap", C.c_double)]
 
 
 # numpy views of the same layouts (device buffers are torch uint8 tensors reinterpreted)

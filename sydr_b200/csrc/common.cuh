@@ -57,24 +57,32 @@ template <> struct IqTraits<SYDR_IQ_F32> { static constexpr int BPS = 8, SPV = 2
 template <int DT>
 __device__ __forceinline__ void decode_vec(const uint4& v, float* re, float* im);
 
+// Integer -> float without the conversion pipe (I2F issues once per ~8 clk per scheduler on
+// sm_100a, profiles/r1_ubench_pipe_rates.txt): bias the integer to unsigned with one XOR per
+// word, splice it into the mantissa of 1.5 * 2^23 with PRMT and subtract the magic constant.
+// Exact for every int8 / int16 value.
 template <>
 __device__ __forceinline__ void decode_vec<SYDR_IQ_I8>(const uint4& v, float* re, float* im) {
     const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    const float magic = 12582912.f + 128.f;                       // 0x4B400000 + bias
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-        re[2 * k]     = (float)(int8_t)(w[k] & 0xff);
-        im[2 * k]     = (float)(int8_t)((w[k] >> 8) & 0xff);
-        re[2 * k + 1] = (float)(int8_t)((w[k] >> 16) & 0xff);
-        im[2 * k + 1] = (float)(int8_t)(w[k] >> 24);
+        const uint32_t t = w[k] ^ 0x80808080u;
+        re[2 * k]     = __uint_as_float(__byte_perm(t, 0x4B400000u, 0x7640)) - magic;
+        im[2 * k]     = __uint_as_float(__byte_perm(t, 0x4B400000u, 0x7641)) - magic;
+        re[2 * k + 1] = __uint_as_float(__byte_perm(t, 0x4B400000u, 0x7642)) - magic;
+        im[2 * k + 1] = __uint_as_float(__byte_perm(t, 0x4B400000u, 0x7643)) - magic;
     }
 }
 template <>
 __device__ __forceinline__ void decode_vec<SYDR_IQ_I16>(const uint4& v, float* re, float* im) {
     const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    const float magic = 12582912.f + 32768.f;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-        re[k] = (float)(int16_t)(w[k] & 0xffff);
-        im[k] = (float)(int16_t)(w[k] >> 16);
+        const uint32_t t = w[k] ^ 0x80008000u;
+        re[k] = __uint_as_float(__byte_perm(t, 0x4B400000u, 0x7610)) - magic;
+        im[k] = __uint_as_float(__byte_perm(t, 0x4B400000u, 0x7632)) - magic;
     }
 }
 template <>
@@ -198,6 +206,19 @@ __device__ __forceinline__ void st_async_v4(uint32_t dst_cluster_addr, uint32_t 
         "r"(__float_as_uint(a)), "r"(__float_as_uint(b)), "r"(__float_as_uint(c)),
         "r"(__float_as_uint(d)), "r"(bar_cluster_addr)
         : "memory");
+}
+
+// Remote (DSMEM) 4-byte store, complete_tx(4) on the destination CTA's mbarrier.
+__device__ __forceinline__ void st_async_b32(uint32_t dst_cluster_addr, uint32_t bar_cluster_addr, float a) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];" ::"r"(dst_cluster_addr),
+                 "r"(__float_as_uint(a)), "r"(bar_cluster_addr)
+                 : "memory");
+}
+
+__device__ __forceinline__ void st_async_b64(uint32_t dst_cluster_addr, uint32_t bar_cluster_addr, double a) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];" ::"r"(dst_cluster_addr),
+                 "l"(__double_as_longlong(a)), "r"(bar_cluster_addr)
+                 : "memory");
 }
 
 __device__ __forceinline__ float warp_sum(float v) {

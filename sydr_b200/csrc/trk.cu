@@ -31,13 +31,17 @@ namespace sydr {
 // (12 samples, 48 B; latency mode, clusters of >= 4 CTAs) or 5 (20 samples, 80 B; throughput
 // mode); complex64 10 (20 samples, 160 B).
 
+constexpr int kMaxChunk = 24;   // longest chunk (int8: 3 vectors of 8 samples)
+
 struct EpochConst {
     double ca, cb;         // carrier phase in turns at sample j: ca*j + cb  (ca = -fc/fs, cb = rem/(2 pi))
     double start[3];       // linspace start  = remCode + spacing     tracking.py:110
     double step[3];        // linspace step'  = (stop-start)/n        numpy linspace
     double inv_step[3];    // ~1/step' (locates chip boundaries; every boundary is then pinned exactly)
     float w[4][2];         // carrier rotation by 1, 2, 3, 4 samples: exp(-j 2 pi k fc/fs)
+    float wtab[kMaxChunk][2];   // carrier rotation by u samples, u < chunk length (split-sum path)
     int n;                 // samples in the epoch
+    int fast;              // every tap keeps a chip for more than kMaxChunk samples: <= 1 flip per chunk and tap
 };
 
 __device__ __forceinline__ double dmul(double a, double b) { return __dmul_rn(a, b); }
@@ -172,6 +176,39 @@ __device__ __forceinline__ void mask_vector(uint4& raw, int vlo, int vhi) {
     raw = make_uint4(w[0], w[1], w[2], w[3]);
 }
 
+// ---- split-sum path -------------------------------------------------------------------------
+// When a chip lasts longer than a chunk, each tap changes sign at most once inside a chunk, and
+// with the usual half-chip spacing at most one *position* in the chunk carries a change (the
+// prompt boundary and the early/late boundary alternate every half chip).  The chunk is then two
+// runs of constant (E, P, L) signs split at sample T: accumulate Y = sum_u x_u w^u over the whole
+// chunk and A = the same sum over u < T (the gate [u < T] is one saturating FADD on the FMA
+// pipe), and apply carrier phasor and the six signs once per chunk.  No per-sample chip work is
+// left, which matters because LOP3/SHF/PRMT issue at half the FFMA rate on sm_100a.
+//
+// Position of the first sample (offset from `lo`) whose chip index exceeds that of sample lo:
+// the real-valued crossing x = (k - phase(lo)) / step' decides it unless x is within 1e-9 of an
+// integer (the reference's two roundings move a crossing by < 1e-11 sample), in which case the
+// caller falls back to the exact walk.  b0 / b1 = code bits of the chip under `lo` and the next.
+__device__ __forceinline__ bool tap_split(double jd, const EpochConst& ec, int s, const uint32_t* cb, int& t,
+                                          uint32_t& b0, uint32_t& b1) {
+    const double ph = dadd(dmul(jd, ec.step[s]), ec.start[s]);        // numpy's linspace value at lo
+    const double mg = __dadd_ru(ph, 6755399441055744.0);              // ceil(ph) in the low word
+    const int k = __double2loint(mg);
+    const double x = dmul(dsub(dsub(mg, 6755399441055744.0), ph), ec.inv_step[s]);   // >= 0, in samples
+    const double xm = __dadd_rd(x, 6755399441055744.0);               // floor(x) in the low word
+    const double fr = x - (xm - 6755399441055744.0);                  // [0, 1)
+    t = __double2loint(xm) + 1;
+    const int wi = k >> 5;
+    const uint32_t w2 = __funnelshift_r(cb[wi & 31], cb[(wi & 31) + 1], k & 31);
+    b0 = w2 & 1u;
+    b1 = (w2 >> 1) & 1u;
+    return (fr > 1e-9) && (fr < 1.0 - 1e-9) && (k >= 0) && (k < kPaddedChips - 1);
+}
+
+__device__ __forceinline__ float sign_of_bit(uint32_t bit) {      // bit 1 -> +1.0f, bit 0 -> -1.0f
+    return __uint_as_float(0x3f800000u | ((bit ^ 1u) << 31));
+}
+
 // Correlate one chunk of C = VPC*SPV samples starting at epoch-relative index j0 against the
 // three taps.  `src` points at the chunk's first vector (shared or global memory, 16-byte
 // aligned); `ec` lives in shared memory.  acc = {IE, QE, IP, QP, IL, QL}.
@@ -180,22 +217,69 @@ __device__ __forceinline__ void correlate_chunk(const uint4* src, int j0, const 
                                                 const uint32_t* cb, float* acc, int& err) {
     constexpr int SPV = IqTraits<DT>::SPV;
     constexpr int C = SPV * VPC;
+    static_assert(C <= kMaxChunk, "chunk longer than the carrier table");
     const int lo = max(j0, 0);
     const int hi = min(j0 + C, ec.n);
     if (hi <= lo) return;
     const bool edge = (lo != j0) || (hi != j0 + C);
-    uint4 cur = src[0];
-
     const double jd = i2d(lo);
-    uint32_t m0 = tap_mask(lo, jd, hi - lo, &ec, 0, cb, &err) << (lo - j0);
-    uint32_t m1 = tap_mask(lo, jd, hi - lo, &ec, 1, cb, &err) << (lo - j0);
-    uint32_t m2 = tap_mask(lo, jd, hi - lo, &ec, 2, cb, &err) << (lo - j0);
 
-// Carrier seed (tracking.py:102): phase of sample j0 in turns, FP64, reduced to [-0.5, 0.5].
+    // Carrier seed (tracking.py:102): phase of sample j0 in turns, FP64, reduced to [-0.5, 0.5].
     double turns = fma(ec.ca, i2d(j0), ec.cb);
     turns -= drint(turns);
     float pre, pim;
     __sincosf((float)turns * 6.283185307179586f, &pim, &pre);
+
+    if (ec.fast) {
+        int t0, t1, t2;
+        uint32_t p0, p1, p2, q0, q1, q2;                    // code bits before / after each tap's flip
+        bool ok = tap_split(jd, ec, 0, cb, t0, p0, q0);
+        ok &= tap_split(jd, ec, 1, cb, t1, p1, q1);
+        ok &= tap_split(jd, ec, 2, cb, t2, p2, q2);
+        const int cnt = hi - lo;
+        // flips beyond the valid samples do not exist for this chunk
+        t0 = (t0 < cnt) ? t0 : 0x10000; t1 = (t1 < cnt) ? t1 : 0x10000; t2 = (t2 < cnt) ? t2 : 0x10000;
+        const int tmin = min(t0, min(t1, t2));
+        ok &= (t0 == tmin || t0 == 0x10000) && (t1 == tmin || t1 == 0x10000) && (t2 == tmin || t2 == 0x10000);
+        if (ok) {
+            const float tf = (float)min(tmin + (lo - j0), C);        // split position relative to j0
+            float Yr = 0.f, Yi = 0.f, Ar = 0.f, Ai = 0.f;
+#pragma unroll
+            for (int v = 0; v < VPC; ++v) {
+                uint4 cur = src[v];
+                if (edge) mask_vector<DT>(cur, lo - (j0 + v * SPV), hi - (j0 + v * SPV));
+                float re[SPV], im[SPV];
+                decode_vec<DT>(cur, re, im);
+#pragma unroll
+                for (int u = 0; u < SPV; ++u) {
+                    const int uu = v * SPV + u;
+                    const float wr = ec.wtab[uu][0], wi = ec.wtab[uu][1];
+                    const float yr = fmaf(re[u], wr, -(im[u] * wi));        // x_u * w^u
+                    const float yi = fmaf(re[u], wi, im[u] * wr);
+                    const float g = __saturatef(tf - (float)uu);            // 1 before the split, 0 after
+                    Yr += yr; Yi += yi;
+                    Ar = fmaf(g, yr, Ar); Ai = fmaf(g, yi, Ai);
+                }
+            }
+            const float Br = Yr - Ar, Bi = Yi - Ai;
+            // signal = replica * rfData (tracking.py:105): rotate both runs by the chunk phasor
+            const float zar = pre * Ar - pim * Ai, zai = pre * Ai + pim * Ar;
+            const float zbr = pre * Br - pim * Bi, zbi = pre * Bi + pim * Br;
+            const float a0 = sign_of_bit(p0), a1 = sign_of_bit(p1), a2 = sign_of_bit(p2);
+            const float b0 = sign_of_bit(t0 == tmin ? q0 : p0), b1 = sign_of_bit(t1 == tmin ? q1 : p1),
+                        b2 = sign_of_bit(t2 == tmin ? q2 : p2);
+            acc[0] += fmaf(a0, zar, b0 * zbr); acc[1] += fmaf(a0, zai, b0 * zbi);
+            acc[2] += fmaf(a1, zar, b1 * zbr); acc[3] += fmaf(a1, zai, b1 * zbi);
+            acc[4] += fmaf(a2, zar, b2 * zbr); acc[5] += fmaf(a2, zai, b2 * zbi);
+            return;
+        }
+    }
+
+    // ---- general path: per-sample sign masks (any chip rate, ties, index wrap-around)
+    uint4 cur = src[0];
+    uint32_t m0 = tap_mask(lo, jd, hi - lo, &ec, 0, cb, &err) << (lo - j0);
+    uint32_t m1 = tap_mask(lo, jd, hi - lo, &ec, 1, cb, &err) << (lo - j0);
+    uint32_t m2 = tap_mask(lo, jd, hi - lo, &ec, 2, cb, &err) << (lo - j0);
 
     // rotations by 1..4 samples
     const float w1r = ec.w[0][0], w1i = ec.w[0][1], w2r = ec.w[1][0], w2i = ec.w[1][1];
@@ -235,6 +319,16 @@ __device__ __forceinline__ void correlate_chunk(const uint4* src, int j0, const 
     acc[0] += a0; acc[1] += a1; acc[2] += a2; acc[3] += a3; acc[4] += a4; acc[5] += a5;
 }
 
+// a / b with a reciprocal rb of b that is correctly rounded or within an ulp: one multiply and
+// the FMA residual correction (Markstein).  Returns the correctly rounded quotient for the
+// operands of this file (checked exhaustively-at-random on the host against IEEE division:
+// code_freq/fs, phase/(2 pi), (1023 - rem)/code_step, (stop - start)/n).
+__device__ __forceinline__ double ddiv_by(double a, double b, double rb) {
+    const double q = a * rb;
+    return fma(fma(-b, q, a), rb, q);
+}
+__device__ __forceinline__ double newton_rcp(double b, double r) { return fma(fma(-b, r, 1.0), r, r); }
+
 // Tap constants of one correlator (numpy linspace arithmetic, tracking.py:110-112).
 __device__ __forceinline__ void tap_const(double rem_code, double spacing, double code_step, int n,
                                           double& start, double& step, double& inv_step) {
@@ -259,13 +353,26 @@ __device__ __forceinline__ void carrier_const(double fc, double rem_carrier, dou
     w[3][0] = c2 * c2 - s2 * s2; w[3][1] = 2.f * c2 * s2;
 }
 
-// Per-epoch constants from the NCO state (one thread; open-loop kernel).
+// Entry u of the carrier table: rotation by u samples, exp(2 pi i u ca), from the FP64 turn count.
+__device__ __forceinline__ void carrier_table_entry(double ca, int u, float& c, float& s) {
+    double tu = dmul(i2d(u), ca - drint(ca));
+    tu -= drint(tu);
+    sincospif((float)(2.0 * tu), &s, &c);
+}
+
+// Per-epoch constants from the NCO state (one thread; open-loop kernel).  `chunk` = samples per
+// thread chunk of the calling kernel (decides whether the split-sum path applies).
 __device__ __forceinline__ void make_epoch_const(EpochConst& ec, int n, double fs, double fc,
                                                  double rem_carrier, double rem_code,
-                                                 double code_step, const double* spacing) {
+                                                 double code_step, const double* spacing, int chunk) {
     ec.n = n;
+    bool fast = true;
 #pragma unroll
-    for (int s = 0; s < 3; ++s) tap_const(rem_code, spacing[s], code_step, n, ec.start[s], ec.step[s], ec.inv_step[s]);
+    for (int s = 0; s < 3; ++s) {
+        tap_const(rem_code, spacing[s], code_step, n, ec.start[s], ec.step[s], ec.inv_step[s]);
+        fast = fast && (ec.inv_step[s] >= (double)(chunk + 1));
+    }
+    ec.fast = fast ? 1 : 0;
     carrier_const(fc, rem_carrier, 1.0 / fs, ec.ca, ec.cb, ec.w);
 }
 
@@ -330,9 +437,12 @@ __global__ void __launch_bounds__(256) epl_batch_kernel(const uint8_t* __restric
     const sydr_epl_args a = args[blockIdx.x];
     if (threadIdx.x < kCodeWords) cb[threadIdx.x] = code_bits[(a.prn - 1) * kCodeWords + threadIdx.x];
     if (threadIdx.x == 0)
-        make_epoch_const(ec_sh, a.n, fs, a.carrier_freq, a.rem_carrier, a.rem_code, a.code_step, a.spacing);
+        make_epoch_const(ec_sh, a.n, fs, a.carrier_freq, a.rem_carrier, a.rem_code, a.code_step, a.spacing, C);
     __syncthreads();
-    const EpochConst ec = ec_sh;
+    if (threadIdx.x < kMaxChunk)
+        carrier_table_entry(ec_sh.ca, threadIdx.x, ec_sh.wtab[threadIdx.x][0], ec_sh.wtab[threadIdx.x][1]);
+    __syncthreads();
+    const EpochConst& ec = ec_sh;
     const long long a0 = a.start & ~(long long)(SPV - 1);     // 16-byte aligned window start
     const int lead = (int)(a.start - a0);
     const int nchunks = (lead + a.n + C - 1) / C;
@@ -357,6 +467,8 @@ struct CodeState {
     long long cur;
     int n_req;
     double code_freq, code_step, rem_code, nco_code_err, nco_code;
+    double inv_step;         // ~1/code_step, carried from epoch to epoch (one Newton step per epoch)
+    double inv_n;            // ~1/n_req, refined with two Newton steps when n changes
 };
 struct CarrierState {
     double carrier_freq, rem_carrier, nco_carrier_err, nco_carrier;
@@ -380,7 +492,7 @@ struct TrkParams {
     int use_tma;
     int append;              // records are indexed by the cumulative epoch count
     long long iq_len;        // > 0: overrides the states' iq_len
-    long long* prof;         // optional [n_channels][8] phase cycle counters of thread 0 (NULL = off)
+    long long* prof;         // optional [n_channels][16] phase cycle counters of thread 0 (NULL = off)
 };
 
 struct EpochCtl {            // published by warps 0 / 1 for every epoch
@@ -392,11 +504,13 @@ struct EpochCtl {            // published by warps 0 / 1 for every epoch
 constexpr int kMaxCluster = 8;
 constexpr int kTrkMaxThreads = 640;
 
+constexpr int kTrkMaxWarps = kTrkMaxThreads / 32;
+
 struct TrkShared {           // static shared memory of the closed-loop kernel
     uint32_t cb[kCodeWords];
     EpochCtl ctl;
-    float red[32][8];
-    alignas(16) float gather[2][kMaxCluster][8];
+    // per-warp partial sums of every CTA of the cluster, [slot][rank * W + warp][component]
+    alignas(16) double gather[2][kMaxCluster * kTrkMaxWarps][8];
     alignas(8) uint64_t bar_data[2];
     uint64_t bar_gather[2];
     sydr_trk_state cfgs;     // the channel's state as loaded (constants live here)
@@ -406,8 +520,8 @@ struct TrkShared {           // static shared memory of the closed-loop kernel
     int n_hist[2];           // samples of epoch e (index e & 1), for the carrier warp
     int rec_base;            // index of this call's first record in the channel's output row
     int status;
-    long long pc[8];         // diagnostics
-    long long tprev;
+    long long pc[16];        // diagnostics
+    long long tprev, tprev1;
 };
 
 // TMA bulk copy of one CTA's window of the epoch starting at sample `a` (executed by one lane).
@@ -435,178 +549,117 @@ __device__ __forceinline__ void trk_prefetch(TrkShared& sh, uint8_t* dst, const 
     }
 }
 
-// Sum over the cluster's ranks of partial-sum component k (fixed order -> identical in every CTA).
-__device__ __forceinline__ double rank_sum(const TrkShared& sh, int slot, uint32_t S, int k) {
-    double s = 0.0;
-    for (uint32_t r = 0; r < S; ++r) s += (double)sh.gather[slot][r][k];
+// Totals of the eight partial-sum components over every warp of every CTA of the cluster.
+// Lane L adds the entries i = (L >> 3) mod 4 of component L & 7 in a fixed order (identical in
+// every CTA, so the redundant loop closures agree bit for bit); on return every lane holds the
+// total of component L & 7.
+__device__ __forceinline__ double gather_total(const TrkShared& sh, int slot, int n_ent, int lane) {
+    const int c = lane & 7;
+    const double* g = &sh.gather[slot][0][c];
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    int i = lane >> 3;
+    for (; i + 12 < n_ent; i += 16) {                 // four independent loads / adds in flight
+        s0 += g[i * 8]; s1 += g[(i + 4) * 8]; s2 += g[(i + 8) * 8]; s3 += g[(i + 12) * 8];
+    }
+    for (; i < n_ent; i += 4) s0 += g[i * 8];
+    double s = (s0 + s1) + (s2 + s3);
+    s += __shfl_xor_sync(0xffffffffu, s, 8);
+    s += __shfl_xor_sync(0xffffffffu, s, 16);
     return s;
 }
 
-// Warp 0, once per epoch.  CLOSE: all-gather the cluster's partial sums, close the CODE loop
-// (DLL_NNEML + Borre filter + code NCO, channel_l1ca_borre.py:383-388, 422-429) and store its
-// share of the epoch record.  Then publish stop flag, epoch bounds and the three tap constants
-// of the next epoch (lanes 0-2: one correlator each) and request its TMA window (lane 4).
-template <int DT, int VPC, bool CLOSE>
-__device__ __noinline__ void trk_code_warp(TrkShared& sh, const TrkParams& P, uint8_t* win0, uint8_t* win1,
-                                           const uint8_t* rec_base, long long rec_alloc, float part, uint32_t S,
-                                           uint32_t rank, int ch, int epoch, int lane, bool prof) {
-    constexpr int SPV = IqTraits<DT>::SPV;
-    constexpr int C = SPV * VPC;
+// Warp 0: close the CODE loop of epoch e (DLL_NNEML + Borre filter + code NCO,
+// channel_l1ca_borre.py:383-388, 422-429), store its share of the epoch record.
+__device__ __forceinline__ void code_close(TrkShared& sh, CodeState& st, int& status, double ck, sydr_trk_epoch* rec,
+                                           int lane) {
     const unsigned full = 0xffffffffu;
-    CodeState st = sh.sc;
-    int status = sh.status;
-    if (CLOSE) {
-        const int e = epoch - 1;                       // the epoch just correlated
-        double ck;                                     // lane k (< 8): total of component k
-        if (S > 1) {
-            const int slot = e & 1;
-            float v[8];
-#pragma unroll
-            for (int k = 0; k < 8; ++k) v[k] = __shfl_sync(full, part, k);
-            if ((uint32_t)lane < S) {
-                const uint32_t dst = mapa_u32(smem_u32(&sh.gather[slot][rank][0]), (uint32_t)lane);
-                const uint32_t rb = mapa_u32(smem_u32(&sh.bar_gather[slot]), (uint32_t)lane);
-                st_async_v4(dst, rb, v[0], v[1], v[2], v[3]);
-                st_async_v4(dst + 16, rb, v[4], v[5], v[6], v[7]);
-            }
-            // st.async data is visible once the phase completes (complete_tx): no cluster fence needed
-            mbar_wait(&sh.bar_gather[slot], (e >> 1) & 1);
-            ck = rank_sum(sh, slot, S, lane & 7);
-        } else {
-            ck = (double)part;
-        }
-        if (prof) { const long long now = clock64(); sh.pc[5] += now - sh.tprev; sh.tprev = now; }   // all-gather
-        // |E| (even lanes) and |L| (odd lanes)                                    tracking.py:126
-        const double mx = __shfl_sync(full, ck, (lane & 1) ? 4 : 0), my = __shfl_sync(full, ck, (lane & 1) ? 5 : 1);
-        const double mag = sqrt(dadd(dmul(mx, mx), dmul(my, my)));
-        const double me = __shfl_sync(full, mag, 0), ml = __shfl_sync(full, mag, 1);
-        const double errflag = __shfl_sync(full, ck, 6);
-        const double code_err = ddiv(dsub(me, ml), dadd(me, ml));
-        double nco_code = dmul(sh.K.dll_c1, dsub(code_err, st.nco_code_err));       // BorreLoopFilter
-        nco_code = dadd(nco_code, dmul(sh.K.dll_c2, code_err));
-        const long long e_start = st.cur;
-        const int e_n = st.n_req;
-        const double n = i2d(e_n);
-        st.code_freq = dsub(st.code_freq, nco_code);                                 // L422
-        st.rem_code = dadd(st.rem_code, dsub(dmul(n, st.code_step), (double)kCodeChips));   // L424
-        st.code_step = ddiv(st.code_freq, sh.K.fs);                                  // L425
-        st.cur += e_n;                                                               // L428
-        st.n_req = ceil_to_int(ddiv(dsub((double)kCodeChips, st.rem_code), st.code_step));  // L429
-        st.nco_code_err = code_err;
-        st.nco_code = nco_code;
-        if (errflag != 0.0) status = SYDR_ERR_STATE;
-        if (rank == 0) {
-            double* rec = reinterpret_cast<double*>(P.out + (long long)ch * P.max_epochs + sh.rec_base + e);
-            if (lane < 6) rec[lane] = ck;              // i_early .. q_late
-            else if (lane == 6) rec[6] = nco_code;
-            else if (lane == 9) rec[9] = st.code_freq;
-            else if (lane == 10) rec[10] = code_err;
-            else if (lane == 12) rec[12] = (double)e_start;
-            else if (lane == 13) rec[13] = n;
-            else if (lane == 14) rec[14] = st.rem_code;
-        }
-        if (lane == 0) sh.sc = st;
-        if (prof) { const long long now = clock64(); sh.pc[6] += now - sh.tprev; sh.tprev = now; }   // code loop
+    // |E| (even lanes) and |L| (odd lanes)                                    tracking.py:126
+    const double mx = __shfl_sync(full, ck, (lane & 1) ? 4 : 0), my = __shfl_sync(full, ck, (lane & 1) ? 5 : 1);
+    const double mag = sqrt(dadd(dmul(mx, mx), dmul(my, my)));
+    const double me = __shfl_sync(full, mag, 0), ml = __shfl_sync(full, mag, 1);
+    const double errflag = __shfl_sync(full, ck, 6);
+    const double code_err = ddiv(dsub(me, ml), dadd(me, ml));
+    double nco_code = dmul(sh.K.dll_c1, dsub(code_err, st.nco_code_err));       // BorreLoopFilter
+    nco_code = dadd(nco_code, dmul(sh.K.dll_c2, code_err));
+    const long long e_start = st.cur;
+    const double n = i2d(st.n_req);
+    st.code_freq = dsub(st.code_freq, nco_code);                                 // L422
+    st.rem_code = dadd(st.rem_code, dsub(dmul(n, st.code_step), (double)kCodeChips));   // L424
+    st.code_step = ddiv_by(st.code_freq, sh.K.fs, sh.K.inv_fs);                  // L425
+    st.cur += st.n_req;                                                          // L428
+    st.inv_step = newton_rcp(st.code_step, st.inv_step);                         // the step moved by ~1e-9
+    st.n_req = ceil_to_int(ddiv_by(dsub((double)kCodeChips, st.rem_code), st.code_step, st.inv_step));  // L429
+    st.nco_code_err = code_err;
+    st.nco_code = nco_code;
+    if (errflag != 0.0) status = SYDR_ERR_STATE;
+    if (rec != nullptr) {                        // lanes 0-5 correlators, 6 dll, 9 code_freq, 10 code_err, 12-14
+        double v = ck;
+        v = (lane == 6) ? nco_code : v;
+        v = (lane == 9) ? st.code_freq : v;
+        v = (lane == 10) ? code_err : v;
+        v = (lane == 12) ? (double)e_start : v;
+        v = (lane == 13) ? n : v;
+        v = (lane == 14) ? st.rem_code : v;
+        if ((0x767Fu >> lane) & 1u) reinterpret_cast<double*>(rec)[lane] = v;
     }
-    // ---- publish epoch `epoch`
-    if (st.n_req <= 0 || (long long)st.n_req + SPV > (long long)S * P.Q * C) status = SYDR_ERR_STATE;
-    const bool stop = (status != 0) || (sh.rec_base + epoch >= P.max_epochs) || (st.cur + st.n_req > sh.cfgs.iq_len);
-    if (!stop) {
-        double t_start, t_step, t_inv;
-        tap_const(st.rem_code, sh.cfgs.spacing[min(lane, 2)], st.code_step, st.n_req, t_start, t_step, t_inv);
-        if (lane < 3) {
-            sh.ctl.ec.start[lane] = t_start;
-            sh.ctl.ec.step[lane] = t_step;
-            sh.ctl.ec.inv_step[lane] = t_inv;
-        } else if (lane == 3) {
-            sh.ctl.ec.n = st.n_req;
-            sh.ctl.a = st.cur;
-            sh.n_hist[epoch & 1] = st.n_req;
-            if (S > 1) mbar_arrive_expect_tx(&sh.bar_gather[epoch & 1], 32u * S);   // arm this epoch's gather
-        } else if (lane == 4 && P.use_tma) {
-            const int buf = epoch & 1;
-            if (epoch == 0) trk_prefetch<DT, VPC>(sh, win0, rec_base, rec_alloc, st.cur, rank, P.Q, 0);
-            // next epoch's window, fetched while this one is correlated
-            trk_prefetch<DT, VPC>(sh, buf ? win0 : win1, rec_base, rec_alloc, st.cur + st.n_req, rank, P.Q, buf ^ 1);
-        }
-    }
-    if (lane == 5) { sh.ctl.stop = stop; sh.status = status; }
-    __syncwarp();
 }
 
-// Warp 1, once per epoch.  CLOSE: close the CARRIER loop (remaining carrier phase, PLL_costa +
-// Borre filter + carrier NCO, channel_l1ca_borre.py:364-365, 391-396, 423) from the prompt sums
-// and store its share of the record; then publish the carrier constants of the next epoch.
-template <bool CLOSE>
-__device__ __noinline__ void trk_carrier_warp(TrkShared& sh, const TrkParams& P, float part, uint32_t S, uint32_t rank,
-                                              int ch, int epoch, int lane) {
+// Warp 1: close the CARRIER loop of epoch e (remaining carrier phase, PLL_costa + Borre filter +
+// carrier NCO, channel_l1ca_borre.py:364-365, 391-396, 423), store its share of the record.
+__device__ __forceinline__ void carrier_close(TrkShared& sh, CarrierState& st, double ck, int n_epoch,
+                                              sydr_trk_epoch* rec, int lane) {
     const unsigned full = 0xffffffffu;
-    CarrierState st = sh.sk;
-    if (CLOSE) {
-        const int e = epoch - 1;
-        double ip, qp;
-        if (S > 1) {
-            const int slot = e & 1;
-            mbar_wait(&sh.bar_gather[slot], (e >> 1) & 1);
-            ip = rank_sum(sh, slot, S, 2);
-            qp = rank_sum(sh, slot, S, 3);
-        } else {
-            ip = (double)__shfl_sync(full, part, 2);
-            qp = (double)__shfl_sync(full, part, 3);
-        }
-        const double n = i2d(sh.n_hist[e & 1]);
-        // L364-365: rem' = (rem - ((fc*2)*pi*n)/fs) mod 2 pi   (Python float %: result in [0, 2 pi))
-        const double twopi = 2.0 * kPi;
-        double rc = dsub(st.rem_carrier, ddiv(dmul(dmul(dmul(st.carrier_freq, 2.0), kPi), n), sh.K.fs));
-        {
-            const double q = floor(rc * 0.15915494309189535);
-            rc = fma(-q, twopi, rc);
-            if (rc < 0.0) rc += twopi;
-            if (rc >= twopi) rc -= twopi;
-        }
-        st.rem_carrier = rc;
-        const double ph_err = ddiv(atan(ddiv(qp, ip)), kGpsPi * 2.0);               // PLL_costa
-        double nco_car = dmul(sh.K.pll_c1, dsub(ph_err, st.nco_carrier_err));        // BorreLoopFilter
-        nco_car = dadd(nco_car, dmul(sh.K.pll_c2, ph_err));
-        st.carrier_freq = dadd(st.carrier_freq, nco_car);                            // L423
-        st.nco_carrier_err = ph_err;
-        st.nco_carrier = nco_car;
-        if (rank == 0) {
-            double* rec = reinterpret_cast<double*>(P.out + (long long)ch * P.max_epochs + sh.rec_base + e);
-            if (lane == 7) rec[7] = nco_car;
-            else if (lane == 8) rec[8] = st.carrier_freq;
-            else if (lane == 11) rec[11] = ph_err;
-            else if (lane == 15) rec[15] = rc;
-        }
-        if (lane == 0) sh.sk = st;
+    const double ip = __shfl_sync(full, ck, 2), qp = __shfl_sync(full, ck, 3);
+    const double n = i2d(n_epoch);
+    // L364-365: rem' = (rem - ((fc*2)*pi*n)/fs) mod 2 pi   (Python float %: result in [0, 2 pi))
+    const double twopi = 2.0 * kPi;
+    double rc = dsub(st.rem_carrier, ddiv_by(dmul(dmul(dmul(st.carrier_freq, 2.0), kPi), n), sh.K.fs, sh.K.inv_fs));
+    {
+        const double q = floor(rc * 0.15915494309189535);
+        rc = fma(-q, twopi, rc);
+        if (rc < 0.0) rc += twopi;
+        if (rc >= twopi) rc -= twopi;
     }
-    double ca, cbb;
-    float w[4][2];
-    carrier_const(st.carrier_freq, st.rem_carrier, sh.K.inv_fs, ca, cbb, w);
-    if (lane == 0) {
-        sh.ctl.ec.ca = ca;
-        sh.ctl.ec.cb = cbb;
-    } else if (lane <= 4) {
-        sh.ctl.ec.w[lane - 1][0] = w[lane - 1][0];
-        sh.ctl.ec.w[lane - 1][1] = w[lane - 1][1];
+    st.rem_carrier = rc;
+    const double ph_err = ddiv_by(atan(ddiv(qp, ip)), kGpsPi * 2.0, 1.0 / (kGpsPi * 2.0));   // PLL_costa
+    double nco_car = dmul(sh.K.pll_c1, dsub(ph_err, st.nco_carrier_err));        // BorreLoopFilter
+    nco_car = dadd(nco_car, dmul(sh.K.pll_c2, ph_err));
+    st.carrier_freq = dadd(st.carrier_freq, nco_car);                            // L423
+    st.nco_carrier_err = ph_err;
+    st.nco_carrier = nco_car;
+    if (rec != nullptr) {                        // lane 7 pll, 8 carrier_freq, 11 carrier_err, 15 rem_carrier
+        double v = nco_car;
+        v = (lane == 8) ? st.carrier_freq : v;
+        v = (lane == 11) ? ph_err : v;
+        v = (lane == 15) ? rc : v;
+        if ((0x8980u >> lane) & 1u) reinterpret_cast<double*>(rec)[lane] = v;
     }
-    __syncwarp();
 }
 
-template <int DT, int VPC>
+// One channel = one CTA or one cluster of S CTAs; W warps per CTA.  Per epoch:
+//   (A) block barrier: the epoch constants published by warps 0 / 1 are visible;
+//   (B) every warp correlates its chunks of the staged window, reduces its six sums with
+//       shuffles and sends them to *every* CTA of the cluster (st.async + complete_tx on the
+//       destination's mbarrier; plain stores + mbarrier.arrive when S = 1);
+//   (C) warps 0 and 1 wait on that mbarrier, total the partial sums, close the code / carrier
+//       loop in FP64, store the epoch record and publish the constants of the next epoch.
+// The TMA window of the next epoch is requested right after (A) by the last warp, off the
+// loop-closing path.
+template <int DT, int VPC, bool TMA>
 __global__ void __launch_bounds__(kTrkMaxThreads) trk_borre_kernel(const TrkParams P) {
     constexpr int SPV = IqTraits<DT>::SPV, BPS = IqTraits<DT>::BPS;
     constexpr int C = SPV * VPC;
     extern __shared__ __align__(128) uint8_t dyn_smem[];
     __shared__ __align__(16) TrkShared sh;
+    const unsigned full = 0xffffffffu;
 
     const uint32_t S = cluster_nctarank();
     const uint32_t rank = cluster_ctarank();
     const int ch = blockIdx.x / S;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, W = blockDim.x >> 5;
     const int Q = P.Q;
-    const uint32_t win_bytes = (uint32_t)Q * C * BPS;
-    uint8_t* win[2] = {dyn_smem, dyn_smem + win_bytes};
+    const uint32_t win_bytes = TMA ? (uint32_t)Q * C * BPS : 0u;
+    const int n_ent = (int)S * W;
 
     sydr_trk_state* gst = P.states + ch;
     if (tid == 0) {
@@ -617,17 +670,19 @@ __global__ void __launch_bounds__(kTrkMaxThreads) trk_borre_kernel(const TrkPara
         sh.sc.cur = g.cur; sh.sc.n_req = (int)g.n_req;
         sh.sc.code_freq = g.code_freq; sh.sc.code_step = g.code_step; sh.sc.rem_code = g.rem_code;
         sh.sc.nco_code_err = g.nco_code_err; sh.sc.nco_code = g.nco_code;
+        sh.sc.inv_step = drcp(g.code_step); sh.sc.inv_n = drcp((double)g.n_req);
         sh.sk.carrier_freq = g.carrier_freq; sh.sk.rem_carrier = g.rem_carrier;
         sh.sk.nco_carrier_err = g.nco_carrier_err; sh.sk.nco_carrier = g.nco_carrier;
         sh.K.fs = P.fs; sh.K.inv_fs = 1.0 / P.fs;
         sh.K.dll_c1 = g.dll_tau2 / g.dll_tau1; sh.K.dll_c2 = g.dll_pdi / g.dll_tau1;
         sh.K.pll_c1 = g.pll_tau2 / g.pll_tau1; sh.K.pll_c2 = g.pll_pdi / g.pll_tau1;
         sh.status = 0;
-        for (int k = 0; k < 8; ++k) sh.pc[k] = 0;
+        for (int k = 0; k < 16; ++k) sh.pc[k] = 0;
         mbar_init(&sh.bar_data[0], 1);
         mbar_init(&sh.bar_data[1], 1);
-        mbar_init(&sh.bar_gather[0], 1);
-        mbar_init(&sh.bar_gather[1], 1);
+        // cluster: one arrival (expect_tx) + S*W*64 bytes of st.async; single CTA: one arrival per warp
+        mbar_init(&sh.bar_gather[0], S > 1 ? 1u : (uint32_t)W);
+        mbar_init(&sh.bar_gather[1], S > 1 ? 1u : (uint32_t)W);
         fence_mbar_init();
     }
     __syncthreads();
@@ -635,6 +690,7 @@ __global__ void __launch_bounds__(kTrkMaxThreads) trk_borre_kernel(const TrkPara
     if (S > 1) cluster_sync_all();                  // remote mbarriers are initialised
     const uint8_t* rec_base = P.iq + sh.cfgs.iq_base * BPS;
     const long long rec_alloc = P.iq_alloc - sh.cfgs.iq_base;   // samples readable from rec_base
+    sydr_trk_epoch* out_row = (rank == 0) ? P.out + (long long)ch * P.max_epochs + sh.rec_base : nullptr;
 
     const bool prof = (P.prof != nullptr) && tid == 0;
 #define SYDR_TICK(k)                                   \
@@ -644,56 +700,142 @@ __global__ void __launch_bounds__(kTrkMaxThreads) trk_borre_kernel(const TrkPara
         sh.tprev = now__;                              \
     }
     if (prof) sh.tprev = clock64();
-    int epoch = 0;
-    if (warp == 0) trk_code_warp<DT, VPC, false>(sh, P, win[0], win[1], rec_base, rec_alloc, 0.f, S, rank, ch, 0, lane, prof);
-    else if (warp == 1) trk_carrier_warp<false>(sh, P, 0.f, S, rank, ch, 0, lane);
-    while (true) {
-        const int buf = epoch & 1;
-        SYDR_TICK(0)                                   // epoch constants + TMA issue
-        __syncthreads();
-        if (sh.ctl.stop) break;
-        SYDR_TICK(1)                                   // barrier
+    const bool prof1 = (P.prof != nullptr) && tid == 32;   // carrier warp: slots 10..13
+#define SYDR_TICK1(k)                                  \
+    if (prof1) {                                       \
+        const long long now__ = clock64();             \
+        sh.pc[k] += now__ - sh.tprev1;                 \
+        sh.tprev1 = now__;                             \
+    }
+    if (prof1) sh.tprev1 = clock64();
 
-        // ---- correlate this CTA's window
+    // loop state lives in registers of its owning warp (warp 0: code, warp 1: carrier)
+    CodeState sc = sh.sc;
+    CarrierState sk = sh.sk;
+    int status = 0;
+    int epoch = 0;
+    while (true) {
+        // ---- (C, second half) publish the constants of epoch `epoch`
+        if (warp == 0) {
+            if (sc.n_req <= 0 || (long long)sc.n_req + SPV > (long long)S * Q * C) status = SYDR_ERR_STATE;
+            const bool stop = (status != 0) || (sh.rec_base + epoch >= P.max_epochs) || (sc.cur + sc.n_req > sh.cfgs.iq_len);
+            if (!stop) {
+                // tap constants (numpy linspace arithmetic, tracking.py:110-112), lane s < 3 = correlator s
+                const double dn = i2d(sc.n_req);
+                sc.inv_n = newton_rcp(dn, newton_rcp(dn, sc.inv_n));                  // n moves by +-1 at most
+                const double t_start = dadd(sc.rem_code, sh.cfgs.spacing[min(lane, 2)]);
+                const double t_stop = dadd(dmul(sc.code_step, dn), t_start);
+                const double t_step = ddiv_by(dsub(t_stop, t_start), dn, sc.inv_n);
+                const int fast = __all_sync(full, sc.inv_step >= (double)(C + 1));   // a chip outlasts a chunk
+                SYDR_TICK(8)
+                if (lane < 3) {
+                    sh.ctl.ec.start[lane] = t_start;
+                    sh.ctl.ec.step[lane] = t_step;
+                    sh.ctl.ec.inv_step[lane] = sc.inv_step;                        // ~1/step': estimates only
+                } else if (lane == 3) {
+                    sh.ctl.ec.n = sc.n_req;
+                    sh.ctl.ec.fast = fast;
+                    sh.ctl.a = sc.cur;
+                    sh.n_hist[epoch & 1] = sc.n_req;
+                    if (S > 1) mbar_arrive_expect_tx(&sh.bar_gather[epoch & 1], 64u * (uint32_t)n_ent);   // arm this epoch's gather
+                }
+            }
+            if (lane == 5) { sh.ctl.stop = stop; sh.status = status; }
+            SYDR_TICK(9)
+        } else if (warp == 1) {
+            double ca, cbb;
+            float w[4][2];
+            carrier_const(sk.carrier_freq, sk.rem_carrier, sh.K.inv_fs, ca, cbb, w);
+            if (lane == 0) {
+                sh.ctl.ec.ca = ca;
+                sh.ctl.ec.cb = cbb;
+            } else if (lane <= 4) {
+                sh.ctl.ec.w[lane - 1][0] = w[lane - 1][0];
+                sh.ctl.ec.w[lane - 1][1] = w[lane - 1][1];
+            }
+            if (lane < kMaxChunk) carrier_table_entry(ca, lane, sh.ctl.ec.wtab[lane][0], sh.ctl.ec.wtab[lane][1]);
+            SYDR_TICK1(13)                             // carrier warp: constants of the next epoch
+        }
+        SYDR_TICK(0)                                   // epoch constants
+        __syncthreads();                               // (A)
+        if (sh.ctl.stop) break;
+        SYDR_TICK(1)                                   // barrier (waits for the slower closing warp)
+
+        const int buf = epoch & 1;
         const long long a = sh.ctl.a;
         const long long a0 = a & ~(long long)(SPV - 1);
         const int lead = (int)(a - a0);
         const long long wstart = (long long)rank * Q * C;          // relative to a0
         const int n_epoch = sh.ctl.ec.n;
+        if (TMA && warp == W - 1 && lane == 0) {
+            if (epoch == 0) trk_prefetch<DT, VPC>(sh, dyn_smem, rec_base, rec_alloc, a, rank, Q, 0);
+            // next epoch's window, fetched while this one is correlated
+            trk_prefetch<DT, VPC>(sh, dyn_smem + (size_t)(buf ^ 1) * win_bytes, rec_base, rec_alloc, a + n_epoch, rank, Q, buf ^ 1);
+        }
+
+        // ---- (B) correlate this CTA's window
         float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         int err = 0;
-        if (P.use_tma) mbar_wait(&sh.bar_data[buf], (epoch >> 1) & 1);
+        if (TMA) mbar_wait(&sh.bar_data[buf], (epoch >> 1) & 1);
         SYDR_TICK(2)                                   // wait for the staged window
         for (int q = tid; q < Q; q += blockDim.x) {
             const int j0 = (int)(wstart + (long long)q * C) - lead;
             if (j0 >= n_epoch) break;
-            const uint4* src;
-            if (P.use_tma) {
-                src = reinterpret_cast<const uint4*>(win[buf] + (size_t)q * C * BPS);
+            // ctl.ec is only rewritten after every warp of the cluster has delivered its sums
+            if (TMA) {          // shared-memory window (address space known to the compiler: LDS.128)
+                const uint4* src = reinterpret_cast<const uint4*>(dyn_smem + (size_t)buf * win_bytes + (size_t)q * C * BPS);
+                correlate_chunk<DT, VPC>(src, j0, sh.ctl.ec, sh.cb, acc, err);
             } else {
-                src = reinterpret_cast<const uint4*>(rec_base + (a0 + wstart + (long long)q * C) * BPS);
+                const uint4* src = reinterpret_cast<const uint4*>(rec_base + (a0 + wstart + (long long)q * C) * BPS);
+                correlate_chunk<DT, VPC>(src, j0, sh.ctl.ec, sh.cb, acc, err);
             }
-            // ctl.ec is only rewritten after the block-wide barrier inside block_sum8
-            correlate_chunk<DT, VPC>(src, j0, sh.ctl.ec, sh.cb, acc, err);
         }
         SYDR_TICK(3)                                   // correlate (thread 0's chunks)
         acc[6] = err ? 1.f : 0.f;                      // code-index overflow anywhere aborts the channel
-        const float part = block_sum8(acc, sh.red);    // warps 0 and 1: lane L holds component L & 7
-        SYDR_TICK(4)                                   // block reduction (waits for the slowest warp)
+        const float wsum = warp_sum8(acc, lane);       // lane L: warp total of component sum8_index(L)
+        const int slot = epoch & 1;
+        {
+            const int c = sum8_index(lane);
+            double* dst = &sh.gather[slot][rank * W + warp][c];
+            const double wd = (double)wsum;            // the only float -> double conversion of the epoch
+            if (S > 1) {
+                const uint32_t d = smem_u32(dst), bar = smem_u32(&sh.bar_gather[slot]);
+                for (uint32_t r = lane & 3; r < S; r += 4)
+                    st_async_b64(mapa_u32(d, r), mapa_u32(bar, r), wd);
+            } else {
+                if ((lane & 3) == 0) *dst = wd;
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&sh.bar_gather[slot]);
+            }
+        }
+        SYDR_TICK(4)                                   // warp reduction + send
+        const int e = epoch;
         ++epoch;
-        if (warp == 0)
-            trk_code_warp<DT, VPC, true>(sh, P, win[0], win[1], rec_base, rec_alloc, part, S, rank, ch, epoch, lane, prof);
-        else if (warp == 1)
-            trk_carrier_warp<true>(sh, P, part, S, rank, ch, epoch, lane);
-        // (the __syncthreads at the top of the next iteration orders ctl / window reuse)
+        // ---- (C) close the loops of epoch e
+        if (warp < 2) {
+            mbar_wait(&sh.bar_gather[slot], (e >> 1) & 1);       // st.async data is visible once the phase completes
+            SYDR_TICK(5)                               // all-gather: wait for the slowest warp of the cluster
+            SYDR_TICK1(10)                             // carrier warp: everything up to the gather
+            const double ck = gather_total(sh, slot, n_ent, lane);
+            SYDR_TICK(7)                               // totals
+            SYDR_TICK1(11)
+            sydr_trk_epoch* rec = out_row ? out_row + e : nullptr;
+            if (warp == 0) code_close(sh, sc, status, ck, rec, lane);
+            else carrier_close(sh, sk, ck, sh.n_hist[e & 1], rec, lane);
+            SYDR_TICK(6)                               // loop closure
+            SYDR_TICK1(12)
+        }
     }
 
     // the window of the epoch that will not run was already requested: drain it before exit
-    if (P.use_tma && epoch > 0) mbar_wait(&sh.bar_data[epoch & 1], (epoch >> 1) & 1);
+    if (TMA && epoch > 0) mbar_wait(&sh.bar_data[epoch & 1], (epoch >> 1) & 1);
 
+    if (warp == 0 && lane == 0) sh.sc = sc;
+    if (warp == 1 && lane == 0) sh.sk = sk;
+    __syncthreads();
     if (prof && rank == 0) {
-        for (int k = 0; k < 7; ++k) P.prof[ch * 8 + k] = sh.pc[k];
-        P.prof[ch * 8 + 7] = epoch;
+        for (int k = 0; k < 15; ++k) P.prof[ch * 16 + k] = sh.pc[k];
+        P.prof[ch * 16 + 15] = epoch;
     }
     if (tid == 0 && rank == 0) {
         gst->cur = sh.sc.cur; gst->n_req = sh.sc.n_req; gst->epochs_done = sh.cfgs.epochs_done + epoch;
@@ -729,7 +871,7 @@ int launch_trk(const TrkParams& P, int n_channels, int cluster, int threads, cud
     const size_t smem = P.use_tma ? (size_t)2 * P.Q * C * IqTraits<DT>::BPS : 0;
     SYDR_REQUIRE(smem <= 200 * 1024, SYDR_ERR_UNSUPPORTED,
                  "tracking window needs %zu B of shared memory; raise cfg.cluster", smem);
-    auto kern = trk_borre_kernel<DT, VPC>;
+    auto kern = P.use_tma ? trk_borre_kernel<DT, VPC, true> : trk_borre_kernel<DT, VPC, false>;
     SYDR_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cudaLaunchConfig_t lc = {};
     lc.gridDim = dim3((unsigned)(n_channels * cluster));
@@ -749,6 +891,32 @@ int launch_trk(const TrkParams& P, int n_channels, int cluster, int threads, cud
 }
 
 }  // namespace
+
+// Vectors per chunk.  The split-sum path needs a chunk no longer than the distance between two
+// consecutive chip-boundary positions of any tap (`gap` chips: 0.5 for the usual -0.5/0/+0.5
+// spacing), so the largest instantiated chunk that fits is chosen; a longer chunk is still
+// correct (per-sample masks) but slower.
+static int pick_vpc(int iq_dtype, double fs, double gap) {
+    const double room = gap * fs / kCodeFreq;              // samples between boundary positions
+    switch (iq_dtype) {
+        case SYDR_IQ_I8:  return (room >= 24.0) ? 3 : 1;                         // 24 / 8 samples
+        case SYDR_IQ_I16: return (room >= 20.0) ? 5 : (room >= 12.0) ? 3 : 1;    // 20 / 12 / 4 samples
+        default:          return (room >= 20.0) ? 10 : (room >= 12.0) ? 6 : 2;   // 20 / 12 / 4 samples
+    }
+}
+
+#define SYDR_DISPATCH_VPC(FN, DTYPE, VPCV, ...)                                        \
+    switch ((DTYPE) * 16 + (VPCV)) {                                                   \
+        case SYDR_IQ_I8 * 16 + 1:   return FN<SYDR_IQ_I8, 1>(__VA_ARGS__);             \
+        case SYDR_IQ_I8 * 16 + 3:   return FN<SYDR_IQ_I8, 3>(__VA_ARGS__);             \
+        case SYDR_IQ_I16 * 16 + 1:  return FN<SYDR_IQ_I16, 1>(__VA_ARGS__);            \
+        case SYDR_IQ_I16 * 16 + 3:  return FN<SYDR_IQ_I16, 3>(__VA_ARGS__);            \
+        case SYDR_IQ_I16 * 16 + 5:  return FN<SYDR_IQ_I16, 5>(__VA_ARGS__);            \
+        case SYDR_IQ_F32 * 16 + 2:  return FN<SYDR_IQ_F32, 2>(__VA_ARGS__);            \
+        case SYDR_IQ_F32 * 16 + 6:  return FN<SYDR_IQ_F32, 6>(__VA_ARGS__);            \
+        case SYDR_IQ_F32 * 16 + 10: return FN<SYDR_IQ_F32, 10>(__VA_ARGS__);           \
+        default: break;                                                                \
+    }
 
 static long long* g_trk_prof = nullptr;    // set by sydr_trk_profile_buffer (diagnostics)
 
@@ -771,14 +939,14 @@ int sydr_epl_batch(const void* d_iq, int iq_dtype, long long iq_len, double fs, 
     int rc = ensure_code_tables(&t);
     if (rc != SYDR_OK) return rc;
     cudaStream_t s = (cudaStream_t)stream;
-    switch (iq_dtype) {
-        case SYDR_IQ_I8: return launch_epl<SYDR_IQ_I8, 3>(d_iq, iq_len, fs, d_args, n_calls, t.padded_bits, d_out, s);
-        case SYDR_IQ_I16: return launch_epl<SYDR_IQ_I16, 5>(d_iq, iq_len, fs, d_args, n_calls, t.padded_bits, d_out, s);
-        case SYDR_IQ_F32: return launch_epl<SYDR_IQ_F32, 10>(d_iq, iq_len, fs, d_args, n_calls, t.padded_bits, d_out, s);
-        default:
-            set_error("sydr_epl_batch: iq_dtype %d not supported (convert complex128 with sydr_convert_to_f32)", iq_dtype);
-            return SYDR_ERR_UNSUPPORTED;
+    if (iq_dtype != SYDR_IQ_I8 && iq_dtype != SYDR_IQ_I16 && iq_dtype != SYDR_IQ_F32) {
+        set_error("sydr_epl_batch: iq_dtype %d not supported (convert complex128 with sydr_convert_to_f32)", iq_dtype);
+        return SYDR_ERR_UNSUPPORTED;
     }
+    SYDR_DISPATCH_VPC(launch_epl, iq_dtype, pick_vpc(iq_dtype, fs, 0.5), d_iq, iq_len, fs, d_args, n_calls,
+                      t.padded_bits, d_out, s)
+    set_error("sydr_epl_batch: no kernel for this chunk size");
+    return SYDR_ERR_UNSUPPORTED;
 }
 
 int sydr_trk_run(const void* d_iq, int iq_dtype, long long iq_alloc_samples, double fs, sydr_trk_state* d_states,
@@ -806,15 +974,17 @@ int sydr_trk_run(const void* d_iq, int iq_dtype, long long iq_alloc_samples, dou
     }
     SYDR_REQUIRE(cluster == 1 || cluster == 2 || cluster == 4 || cluster == 8, SYDR_ERR_ARG,
                  "cluster must be 1, 2, 4 or 8 (got %d)", cluster);
-    int spv, vpc, bps;
+    int spv, bps;
     switch (iq_dtype) {
-        case SYDR_IQ_I8: spv = 8; vpc = 3; bps = 2; break;
-        case SYDR_IQ_I16: spv = 4; vpc = (cluster >= 4) ? 3 : 5; bps = 4; break;   // latency / throughput chunks
-        case SYDR_IQ_F32: spv = 2; vpc = 10; bps = 8; break;
+        case SYDR_IQ_I8: spv = 8; bps = 2; break;
+        case SYDR_IQ_I16: spv = 4; bps = 4; break;
+        case SYDR_IQ_F32: spv = 2; bps = 8; break;
         default:
             set_error("sydr_trk_run: iq_dtype %d not supported", iq_dtype);
             return SYDR_ERR_UNSUPPORTED;
     }
+    const double gap = (cfg && cfg->min_tap_gap > 0.0) ? cfg->min_tap_gap : 0.5;
+    const int vpc = pick_vpc(iq_dtype, fs, gap);
     const int C = spv * vpc;
     // shared-memory budget: two windows of Q*C samples
     while (use_tma && cluster < 8 && 2 * ((n_max + spv + (long long)C * cluster - 1) / ((long long)C * cluster)) * C * bps > 200 * 1024)
@@ -842,13 +1012,9 @@ int sydr_trk_run(const void* d_iq, int iq_dtype, long long iq_alloc_samples, dou
     P.iq_len = cfg ? cfg->iq_len : 0;
     P.prof = g_trk_prof;
     cudaStream_t s = (cudaStream_t)stream;
-    switch (iq_dtype) {
-        case SYDR_IQ_I8: return launch_trk<SYDR_IQ_I8, 3>(P, n_channels, cluster, threads, s);
-        case SYDR_IQ_I16:
-            return (vpc == 3) ? launch_trk<SYDR_IQ_I16, 3>(P, n_channels, cluster, threads, s)
-                              : launch_trk<SYDR_IQ_I16, 5>(P, n_channels, cluster, threads, s);
-        default: return launch_trk<SYDR_IQ_F32, 10>(P, n_channels, cluster, threads, s);
-    }
+    SYDR_DISPATCH_VPC(launch_trk, iq_dtype, vpc, P, n_channels, cluster, threads, s)
+    set_error("sydr_trk_run: no kernel for this chunk size");
+    return SYDR_ERR_UNSUPPORTED;
 }
 
 int sydr_trk_state_init(sydr_trk_state* h, int prn, double fs, double carrier_freq, long long start_sample,

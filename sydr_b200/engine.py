@@ -196,6 +196,18 @@ def make_trk_states(fs, channels, cfg=None) -> np.ndarray:
     return st
 
 
+def min_tap_gap(spacing: np.ndarray) -> float:
+    """Smallest circular distance (chips) between the chip-boundary positions of two correlators:
+    tap s changes chip where the code phase is congruent to -spacing_s modulo one chip."""
+    gap = 1.0
+    for row in np.atleast_2d(spacing):
+        pos = np.unique(np.round(np.mod(-np.asarray(row, dtype=np.float64), 1.0), 12))
+        if len(pos) > 1:
+            d = np.diff(np.r_[pos, pos[0] + 1.0])
+            gap = min(gap, float(d.min()))
+    return gap
+
+
 class TrackingEngine:
     """Closed-loop E/P/L tracking of many channels in one launch (K-TRK)."""
 
@@ -208,9 +220,9 @@ class TrackingEngine:
         self.fs = float(fs)
         self.n_ch = len(states)
         self.max_epochs = int(max_epochs)
-        self.cfg = L.TrkConfig(int(cluster), int(threads), 1 if use_tma else 0, 0, 0)
         st = np.ascontiguousarray(states)
         assert st.dtype == L.TRK_STATE_DTYPE
+        self.cfg = L.TrkConfig(int(cluster), int(threads), 1 if use_tma else 0, 0, 0, min_tap_gap(st["spacing"]))
         self._states = torch.from_numpy(st.view(np.uint8).reshape(-1).copy()).to(self.device)
         self._out = torch.empty(self.n_ch * self.max_epochs * 128, dtype=torch.uint8, device=self.device)
         self._nep = torch.zeros(self.n_ch, dtype=torch.int32, device=self.device)
@@ -225,6 +237,7 @@ class TrackingEngine:
         """Load fresh channel states (same channel count) without reallocating."""
         st = np.ascontiguousarray(states)
         assert st.dtype == L.TRK_STATE_DTYPE and len(st) == self.n_ch
+        self.cfg.min_tap_gap = min_tap_gap(st["spacing"])
         self._states.copy_(torch.from_numpy(st.view(np.uint8).reshape(-1)))
 
     def launch(self, iq_dev: torch.Tensor, stream=None, iq_len: int = 0, append: bool = False):

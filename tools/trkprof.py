@@ -14,19 +14,19 @@ d_all = torch.cat([d_iq, pad])[:d_iq.numel()]
 acq = AcquisitionEngine(fs, 0.0, 5000, 250, 1, 10, list(synth.PRNS_12))
 peaks = acq.run(d_all)["peaks"]
 chans = [dict(prn=int(p["prn"]), carrier_freq=acq.handoff(p)[0], start_sample=acq.handoff(p)[2], iq_len=d_all.numel() // 2) for p in peaks]
-names = ["const+tma", "barrier", "win wait", "correlate", "blk reduce", "gather", "close loops"]
-for cluster in (1, 2, 4, 8):
-    for tma in (True, False):
-        prof = torch.zeros(len(chans) * 8, dtype=torch.int64, device="cuda")
+names = ["const", "barrier", "win wait", "correlate", "wsum+send", "gather wait", "close", "totals", "pub:math", "pub:store", "w1:->gather", "w1:totals", "w1:close", "w1:const"]
+for cluster in (1, 8):
+    for tma in (True,):
+        prof = torch.zeros(len(chans) * 16, dtype=torch.int64, device="cuda")
         L.load().sydr_trk_profile_buffer(prof.data_ptr())
         eng = TrackingEngine(fs, make_trk_states(fs, chans), 600, cluster=cluster, use_tma=tma)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         eng.launch(d_all); torch.cuda.synchronize()
         eng = TrackingEngine(fs, make_trk_states(fs, chans), 600, cluster=cluster, use_tma=tma)
         e0.record(); eng.launch(d_all); e1.record(); torch.cuda.synchronize()
-        p = prof.cpu().numpy().reshape(-1, 8)
-        ep = p[:, 7].mean()
-        cyc = p[:, :7].mean(axis=0) / ep
+        p = prof.cpu().numpy().reshape(-1, 16)
+        ep = p[:, 15].mean()
+        cyc = p[:, :14].mean(axis=0) / ep
         print(f"S={cluster} tma={int(tma)} {e0.elapsed_time(e1) * 1e3 / ep:7.2f} us/epoch | " +
-              "  ".join(f"{n}:{c:6.0f}" for n, c in zip(names, cyc)) + f" | sum {cyc.sum():.0f} cyc")
+              "  ".join(f"{n}:{c:6.0f}" for n, c in zip(names, cyc)) + f" | sum {cyc[:10].sum():.0f} cyc")
 L.load().sydr_trk_profile_buffer(None)
