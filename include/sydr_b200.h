@@ -144,7 +144,8 @@ typedef struct {
     int64_t n_req;          /* track_requiredSamples                                        */
     int64_t epochs_done;    /* epochs processed so far (all launches)                       */
     int32_t prn;
-    int32_t status;         /* 0 ok; <0 = channel aborted (SYDR_ERR_STATE)                  */
+    int32_t status;         /* 0 ok; <0 = channel aborted (SYDR_ERR_STATE); >0 = idle slot:
+                               the kernel leaves the channel untouched                      */
     double  carrier_freq;   /* carrierFrequency                                             */
     double  code_freq;      /* codeFrequency                                                */
     double  code_step;      /* codeStep                                                     */

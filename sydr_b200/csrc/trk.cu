@@ -676,7 +676,7 @@ __global__ void __launch_bounds__(kTrkMaxThreads) trk_borre_kernel(const TrkPara
         sh.K.fs = P.fs; sh.K.inv_fs = 1.0 / P.fs;
         sh.K.dll_c1 = g.dll_tau2 / g.dll_tau1; sh.K.dll_c2 = g.dll_pdi / g.dll_tau1;
         sh.K.pll_c1 = g.pll_tau2 / g.pll_tau1; sh.K.pll_c2 = g.pll_pdi / g.pll_tau1;
-        sh.status = 0;
+        sh.status = sh.cfgs.status;
         for (int k = 0; k < 16; ++k) sh.pc[k] = 0;
         mbar_init(&sh.bar_data[0], 1);
         mbar_init(&sh.bar_data[1], 1);
@@ -712,7 +712,7 @@ __global__ void __launch_bounds__(kTrkMaxThreads) trk_borre_kernel(const TrkPara
     // loop state lives in registers of its owning warp (warp 0: code, warp 1: carrier)
     CodeState sc = sh.sc;
     CarrierState sk = sh.sk;
-    int status = 0;
+    int status = sh.cfgs.status;                   // != 0: aborted earlier (< 0) or idle slot (> 0): no epochs
     int epoch = 0;
     while (true) {
         // ---- (C, second half) publish the constants of epoch `epoch`

@@ -265,8 +265,8 @@ class TrackingEngine:
         self.launch(iq_dev, stream=stream)
         res = self.fetch()
         st = self.states()
-        if (st["status"] != 0).any():
-            bad = np.nonzero(st["status"])[0].tolist()
+        if (st["status"] < 0).any():
+            bad = np.nonzero(st["status"] < 0)[0].tolist()
             raise L.SydrError(f"tracking aborted on channels {bad} (NCO state left the supported range)")
         return res
 

@@ -253,12 +253,114 @@ def g_loop(R):
     save("loop.npz", **out)
 
 
+def g_channel(R):
+    """Per-tick packet schedule of the live reference channel (types, flags, unread samples) and
+    a random-operation trace of the reference CircularBuffer."""
+    C = ref_import.load_channel()
+    out = {}
+    fs, nbits, seed, ms, prns, ds = 4e6, 8, 21, 700, (3, 7), 250          # the "fs4" case of loop.npz
+    sc = synth.make_scenario(fs, nbits, ms * 1e-3, prns, seed, float(ds))
+    iq = synth.generate_iq(sc)
+    x = synth.to_complex(iq)
+    acq_cfg = {"doppler_range": "5000", "doppler_steps": str(ds), "coherent_integration": "1",
+               "non_coherent_integration": "10", "threshold": "1.5"}
+    for prn in prns:
+        cfg = {"filepath": "none", "sampling_frequency": str(fs), "is_complex": "true",
+               "intermediate_frequency": "0.0", "data_size": "8"}
+        rf = C.RFSignal(cfg)
+        spm = rf.samplesPerMs
+        buf = C.CircularBuffer(int(fs * 1e-3 * 100), np.complex128)
+        ch = C.ChannelL1CA(0, buf, None, rf, {"ACQUISITION": acq_cfg, "TRACKING": TRK_CFG})
+        ch.setSatellite(prn)
+        rows = []
+        for tick in range(ms):
+            buf.shift(x[tick * spm:(tick + 1) * spm])
+            res = ch._processHandler()
+            upd = ch.prepareChannelUpdate()
+            types = [r["type"] for r in res]
+            rows.append([types.count(C.ChannelMessage.ACQUISITION_UPDATE), types.count(C.ChannelMessage.TRACKING_UPDATE),
+                         types.count(C.ChannelMessage.DECODING_UPDATE), upd["state"].value, int(upd["tracking_flags"]),
+                         upd["time_since_tow"], upd["unprocessed_samples"], upd["code_since_tow"], ch.currentSample,
+                         ch.nbPrompt, ch.navBitsCounter])
+        out[f"ticks_{prn}"] = np.array(rows, dtype=np.float64)
+        out[f"navbits_{prn}"] = np.array(ch.navBitsBuffer[:ch.navBitsCounter], dtype=np.int8)
+    out["meta"] = np.array([fs, nbits, seed, ms, ds], dtype=np.float64)
+    out["prns"] = np.array(prns)
+    out["sha"] = sha(iq)
+    # CircularBuffer trace: shifts of 50 into a ring of 400, slices and unread counts at random positions
+    rng = np.random.default_rng(9)
+    cb = C.CircularBuffer(400, np.float64)
+    trace = []
+    for k in range(30):
+        cb.shift(np.arange(k * 50, (k + 1) * 50, dtype=np.float64))
+        cur = int(rng.integers(0, 400))
+        nreq = int(rng.integers(1, 120))
+        sl = cb.getSlice(cur, nreq)
+        trace.append([cb.idxWrite, cb.size, int(cb.full), cur, nreq, cb.getNbUnreadSamples(cur), sl.shape[1],
+                      float(np.nansum(sl[:, :min(5, sl.shape[1])]))])
+    out["ring_trace"] = np.array(trace, dtype=np.float64)
+    save("channel.npz", **out)
+
+
+def g_decoding(R):
+    """Inputs and the reference's outputs for LNAV_CheckPreambule / LNAV_DecodeTOW / Prompt2Bit."""
+    from sydr.dsp import decoding as RD
+    from sydr_b200.dsp.decoding import _PARITY_TAPS
+    rng = np.random.default_rng(17)
+
+    def word(prev2, data24):
+        src = list(prev2) + list(data24)
+        par = []
+        for taps in _PARITY_TAPS:
+            b = 0
+            for t in taps:
+                b ^= src[t]
+            par.append(b)
+        return [int(b) ^ int(prev2[1]) for b in data24] + par
+
+    wins, exp = [], []
+    pre = [1, 0, 0, 0, 1, 0, 1, 1]
+    for trial in range(600):
+        if trial % 3 == 0:
+            bits = rng.integers(0, 2, 62)
+        else:
+            prev = [int(v) for v in rng.integers(0, 2, 2)]
+            d1 = [b ^ prev[1] for b in pre] + [int(v) for v in rng.integers(0, 2, 16)]
+            if trial % 2:
+                d1 = [1 - b for b in d1[:8]] + d1[8:]
+            w1 = word(prev, d1)
+            w2 = word(w1[-2:], [int(v) for v in rng.integers(0, 2, 24)])
+            bits = np.array(prev + w1 + w2)
+            if trial % 7 == 0:
+                bits[int(rng.integers(10, 62))] ^= 1
+        wins.append(np.array(bits, dtype=np.int64))
+        exp.append(bool(RD.LNAV_CheckPreambule(np.array(bits, dtype=np.int64).copy())))
+    sfs, tows = [], []
+    for trial in range(60):
+        sf = rng.integers(0, 2, 300).astype(np.int64)
+        d = int(rng.integers(0, 2))
+        tow, sid, txt = RD.LNAV_DecodeTOW(sf.copy(), d)
+        sfs.append(np.r_[d, sf])
+        tows.append([tow, sid] + [int(c) for c in txt])
+    save("decoding.npz", windows=np.array(wins, dtype=np.int8), check=np.array(exp),
+         subframes=np.array(sfs, dtype=np.int8), tow=np.array(tows, dtype=np.int32),
+         p2b=np.array([RD.Prompt2Bit(v) for v in (-3.0, 0.0, 2.5)]))
+
+
+TRK_CFG = {
+    "correlator_early": "-0.5", "correlator_prompt": "0", "correlator_late": "0.5",
+    "dll_damping_ratio": "0.7", "dll_noise_bandwidth": "1.0", "dll_loop_gain": "1.0", "dll_pdi": "0.001",
+    "pll_damping_ratio": "0.7", "pll_noise_bandwidth": "8.0", "pll_loop_gain": "0.25", "pll_pdi": "0.001",
+    "fll_damping_ratio": "0.7", "fll_noise_bandwidth": "15.0", "fll_loop_gain": "1.5", "fll_pdi": "0.001"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--only", nargs="*", default=None)
     a = ap.parse_args()
     R = ref_import.load()
-    groups = {"codes": g_codes, "peaks": g_peaks, "acq": g_acq, "epl": g_epl, "loop": g_loop}
+    groups = {"codes": g_codes, "peaks": g_peaks, "acq": g_acq, "epl": g_epl, "loop": g_loop, "channel": g_channel,
+              "decoding": g_decoding}
     for name, fn in groups.items():
         if a.only and name not in a.only and not (name == "acq" and any(o in ACQ_CASES for o in a.only)):
             continue

@@ -1,0 +1,93 @@
+"""Host-side mirrors of the reference's interfaces (no GPU needed): ring-buffer index arithmetic,
+IQ file reader, navigation-bit helpers, enumerations -- against fixtures produced by the
+reference's own classes (tests/golden/make_golden.py: g_channel, g_decoding)."""
+import numpy as np
+import pytest
+
+import helpers as H
+
+
+def test_circular_buffer_matches_reference_trace(golden):
+    from sydr_b200.utils.circularbuffer import CircularBuffer
+    tr = golden("channel.npz")["ring_trace"]
+    rng = np.random.default_rng(9)
+    cb = CircularBuffer(400, np.float64)
+    for k, row in enumerate(tr):
+        cb.shift(np.arange(k * 50, (k + 1) * 50, dtype=np.float64))
+        cur = int(rng.integers(0, 400))
+        nreq = int(rng.integers(1, 120))
+        sl = cb.getSlice(cur, nreq)
+        got = [cb.idxWrite, cb.size, int(cb.full), cur, nreq, cb.getNbUnreadSamples(cur), sl.shape[1],
+               float(np.nansum(sl[:, :min(5, sl.shape[1])]))]
+        assert got[:7] == [int(v) for v in row[:7]]
+        if k >= 8:                       # before the ring is full the reference reads uninitialised memory
+            assert got[7] == row[7]
+    with pytest.raises(ValueError):
+        cb.shift(np.zeros(33))
+    nostore = CircularBuffer(400, np.float64, store=False)
+    nostore.shiftIdxWrite(50)
+    assert nostore.idxWrite == 50 and nostore.getNbUnreadSamples(10) == 40
+    with pytest.raises(RuntimeError):
+        nostore.getSlice(0, 10)
+
+
+def test_decoding_helpers_match_reference(golden):
+    from sydr_b200.dsp.decoding import LNAV_CheckPreambule, LNAV_DecodeTOW, Prompt2Bit
+    g = golden("decoding.npz")
+    got = [LNAV_CheckPreambule(w.astype(np.int64)) for w in g["windows"]]
+    assert got == [bool(v) for v in g["check"]] and sum(got) > 100
+    for row, exp in zip(g["subframes"], g["tow"]):
+        sf = row[1:].astype(np.int64)
+        tow, sid, txt = LNAV_DecodeTOW(sf, int(row[0]))
+        assert (tow, sid) == (int(exp[0]), int(exp[1])) and [int(c) for c in txt] == [int(v) for v in exp[2:]]
+        assert [int(v) for v in sf] == [int(v) for v in exp[2:]]          # corrected in place, like the reference
+    assert [Prompt2Bit(v) for v in (-3.0, 0.0, 2.5)] == [int(v) for v in g["p2b"]]
+
+
+@pytest.mark.parametrize("bits", [8, 16])
+def test_rfsignal_reader(tmp_path, bits):
+    from sydr_b200.signal.rfsignal import IQBlock, RFSignal
+    fs = 2e6
+    dt = np.int8 if bits == 8 else np.int16
+    rng = np.random.default_rng(bits)
+    raw = rng.integers(-100, 100, size=2 * int(fs * 0.3)).astype(dt)
+    path = tmp_path / "iq.bin"
+    raw.tofile(path)
+    rf = RFSignal({"filepath": str(path), "sampling_frequency": str(fs), "is_complex": "true",
+                   "intermediate_frequency": "0.0", "data_size": str(bits)})
+    assert rf.samplesPerMs == 2000 and rf.dtype == np.complex128 and rf.fileDataType == dt
+    ref = raw[0::2] + 1j * raw[1::2]
+    pos = 0
+    for _ in range(130):                           # crosses the 120 ms chunk boundary
+        blk = rf.getMilliseconds(1)
+        assert isinstance(blk, IQBlock) and blk.dtype == np.complex128 and len(blk) == 2000
+        assert np.array_equal(blk, ref[pos:pos + 2000]) and np.array_equal(blk.raw, raw[2 * pos:2 * pos + 4000])
+        pos += 2000
+    assert rf.getCurrentSampleIndex() == int(2 * 240 * 2000 * np.dtype(dt).itemsize / 2)
+    with pytest.raises(ValueError):
+        rf.getMilliseconds(7)
+    rf.closeFile()
+    with pytest.raises(Warning):
+        rf.closeFile()
+    again = RFSignal({"filepath": str(path), "sampling_frequency": str(fs), "is_complex": "true",
+                      "intermediate_frequency": "0.0", "data_size": str(bits)})
+    part = again.readFileBySamples(100, skip=50)
+    assert np.array_equal(part, ref[50:150])
+    with pytest.raises(ValueError):
+        RFSignal({"filepath": "x", "sampling_frequency": "1e6", "is_complex": "true",
+                  "intermediate_frequency": "0", "data_size": "4"})
+
+
+def test_enumerations_have_reference_values():
+    from sydr_b200.utils.enumerations import ChannelMessage, ChannelState, GNSSSignalType, TrackingFlags
+    assert [m.value for m in ChannelMessage] == [0, 1, 2, 3, 4]
+    assert ChannelState.TRACKING.value == 3 and str(ChannelState.ACQUIRING) == "ACQUIRING"
+    assert TrackingFlags.CODE_LOCK | TrackingFlags.BIT_SYNC == 3 and int(TrackingFlags.FINE_LOCK) == 128
+    assert str(GNSSSignalType.GPS_L1_CA) == "GPS L1 CA"
+
+
+def test_min_tap_gap():
+    from sydr_b200.engine import min_tap_gap
+    assert min_tap_gap(np.array([[-0.5, 0.0, 0.5]])) == 0.5
+    assert abs(min_tap_gap(np.array([[-0.25, 0.0, 0.25]])) - 0.25) < 1e-12
+    assert abs(min_tap_gap(np.array([[-0.5, 0.0, 0.5], [-0.1, 0.0, 0.1]])) - 0.1) < 1e-12
