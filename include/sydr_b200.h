@@ -202,6 +202,11 @@ int sydr_trk_run(const void* d_iq, int iq_dtype, long long iq_alloc_samples, dou
  * reduction + send, gather wait, loop closure, gather totals; [15] = epochs).  NULL = off. */
 int sydr_trk_profile_buffer(long long* d_buf);
 
+/* Diagnostics / tests: which correlator formulation K-TRK uses.  0 (default) = automatic: the
+ * half-chip segment path wherever the spacings are multiples of half a chip and the sampling
+ * rate fits, else the chunk paths; 1 = chunk paths only.  Results agree to rounding. */
+int sydr_trk_set_mode(int mode);
+
 /* Host helper: initial state exactly as ChannelL1CA leaves it after acquisition
  * (channel_l1ca_borre.py:110-120, 250-251, 301-311). */
 int sydr_trk_state_init(sydr_trk_state* h_state, int prn, double fs, double carrier_freq,

@@ -109,6 +109,7 @@ SIGNATURES = {
     "sydr_epl_batch": (_i, [_vp, _i, _ll, _d, _vp, _i, _vp, _vp]),
     "sydr_trk_run": (_i, [_vp, _i, _ll, _d, _vp, _i, _vp, _i, _vp, _vp, _vp]),
     "sydr_trk_profile_buffer": (_i, [_vp]),
+    "sydr_trk_set_mode": (_i, [_i]),
     "sydr_trk_state_init": (_i, [_vp, _i, _d, _d, _ll] + [_d] * 11),
     "sydr_convert_to_f32": (_i, [_vp, _i, _ll, _vp, _vp]),
     # legacy per-call ABI (sydr/c_functions/*.c)

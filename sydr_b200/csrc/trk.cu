@@ -42,6 +42,8 @@ struct EpochConst {
     float wtab[kMaxChunk][2];   // carrier rotation by u samples, u < chunk length (split-sum path)
     int n;                 // samples in the epoch
     int fast;              // every tap keeps a chip for more than kMaxChunk samples: <= 1 flip per chunk and tap
+    int seg;               // half-chip segment path applies to this epoch (see correlate_segment)
+    int hb;                // first half-chip lattice index this CTA looks at
 };
 
 __device__ __forceinline__ double dmul(double a, double b) { return __dmul_rn(a, b); }
@@ -319,6 +321,188 @@ __device__ __forceinline__ void correlate_chunk(const uint4* src, int j0, const 
     acc[0] += a0; acc[1] += a1; acc[2] += a2; acc[3] += a3; acc[4] += a4; acc[5] += a5;
 }
 
+// ---- half-chip segment path ------------------------------------------------------------------
+// With correlator spacings that are multiples of half a chip (the reference's -0.5 / 0 / +0.5,
+// channel_GPS_L1CA_borre.ini:14-16 and channel_GPS_L1CA_kaplan.ini:13-14) every tap changes
+// chip only where the prompt code phase crosses a multiple of 0.5: between two consecutive
+// lattice points h-1 and h the three code values are constant.  One thread therefore owns one
+// *segment* H (the samples with (H-1)/2 < phase <= H/2, ~12.2 at 25 MS/s): it sums
+// x_u w^u over the segment with a two-chain Horner recurrence in packed FP32 (FFMA2), rotates
+// the sum by the carrier phasor of its first sample and adds it to E, P and L with the three
+// signs of the segment, which come from a per-channel table indexed by H (code index of tap s =
+// ceil((H + q_s) / 2), q_s = 2 (spacing_s - spacing_prompt)).  There is no per-sample chip,
+// gate or table work at all.
+//
+// Exactness.  The first sample of segment h+1 is B(h) = min{ j : phase(j) > h/2 }.  It is
+// located from the real-valued crossing X(h) = (h/2 - start) / step', whose distance to the
+// decision boundary of the reference expression ceil(fl(fl(j step') + start)) is < 1e-10
+// sample for every tap; when X(h) is within 1e-9 of an integer J the sample J is given to
+// segment h+1 and its three code indices are evaluated with the reference expression itself
+// (seg_correct), so every sample carries exactly the chip the reference gives it.
+constexpr int kSegTab = 2080;                 // lattice indices 0 .. 2079 (an epoch touches <= 2048)
+constexpr double kMagic52 = 6755399441055744.0;   // 1.5 * 2^52
+
+// Lattice crossing X(h) in samples: every thread that needs it evaluates this very expression.
+__device__ __forceinline__ double seg_crossing(double hd_half, double start, double inv_step) {
+    return dmul(dsub(hd_half, start), inv_step);
+}
+// B(h) = floor(X) + 1, or floor(X) when X is within 1e-9 above an integer; amb = X within 1e-9 of
+// an integer (the sample B(h) then needs the exact evaluation).
+__device__ __forceinline__ int seg_first_sample(double x, bool& amb) {
+    const double xm = __dadd_rd(x, kMagic52);
+    const double fr = x - (xm - kMagic52);                  // [0, 1)
+    const bool low = fr < 1e-9;
+    amb = low || (fr > 1.0 - 1e-9);
+    return __double2loint(xm) + (low ? 0 : 1);
+}
+
+// Signs of the three taps for every lattice index: bit s of tab[H] = padded-code bit of tap s.
+__device__ __forceinline__ void build_seg_table(uint8_t* tab, const uint32_t* cb, const int* q) {
+    for (int H = threadIdx.x; H < kSegTab; H += blockDim.x) {
+        uint32_t b = 0;
+#pragma unroll
+        for (int s = 0; s < 3; ++s) {
+            const int k = min(max((H + q[s] + 1) >> 1, 0), kPaddedChips - 1);
+            b |= ((cb[k >> 5] >> (k & 31)) & 1u) << s;
+        }
+        tab[H] = (uint8_t)b;
+    }
+}
+// q_s = 2 (spacing_s - spacing_prompt) when every spacing is a multiple of half a chip around the
+// prompt tap; returns false otherwise (the chunk paths then serve the channel).
+__device__ __forceinline__ bool seg_tap_offsets(const double* spacing, int* q) {
+    bool ok = true;
+#pragma unroll
+    for (int s = 0; s < 3; ++s) {
+        const double d = 2.0 * (spacing[s] - spacing[1]);
+        const double r = drint(d);
+        ok = ok && (d == r) && (fabs(r) <= 8.0);
+        q[s] = (int)r;
+    }
+    return ok;
+}
+
+// Exact treatment of an ambiguous first sample J of segment h (rare): replace the segment's
+// signs by the code values the reference expression gives, tap by tap.
+__device__ __noinline__ void seg_correct(uint32_t raw, int J, int h, float pr, float pi, const EpochConst* ec,
+                                         const int* q, const uint32_t* cb, float* acc, int* err) {
+    const uint32_t t = raw ^ 0x80008000u;
+    const float magic = 12582912.f + 32768.f;
+    const float xr = __uint_as_float(__byte_perm(t, 0x4B400000u, 0x7610)) - magic;
+    const float xi = __uint_as_float(__byte_perm(t, 0x4B400000u, 0x7632)) - magic;
+    const float zr = pr * xr - pi * xi, zi = pr * xi + pi * xr;
+    int e = 0;
+    for (int s = 0; s < 3; ++s) {
+        const int k_exact = ceil_to_int(code_phase(J, ec->start[s], ec->step[s]));
+        const int k_seg = (h + q[s] + 1) >> 1;
+        if (k_exact == k_seg) continue;
+        const float d = sign_of_bit(chip_bit(cb, k_exact, e)) - sign_of_bit(chip_bit(cb, k_seg, e));
+        acc[2 * s] = fmaf(d, zr, acc[2 * s]);
+        acc[2 * s + 1] = fmaf(d, zi, acc[2 * s + 1]);
+    }
+    if (e) *err = 1;
+}
+
+// One segment of int16 IQ.  `base` points at the sample whose epoch-relative index is `wlo`
+// (8-byte aligned: shared-memory window or global memory); the thread owns segment h if its first
+// sample lies in [wlo, whi).  NV 8-byte loads cover the segment (<= 2 NV - 1 samples from an even
+// address); LMIN = 2 NV - 2 is the shortest unclipped segment of this instantiation.
+// Returns false once the segment starts at or beyond min(whi, n): the caller's loop over h ends.
+template <int NV>
+__device__ __forceinline__ bool correlate_segment(const uint8_t* base, int wlo, int whi, int h, const EpochConst& ec,
+                                                  const uint8_t* tab, const int* q, const uint32_t* cb, float* acc,
+                                                  int& err) {
+    constexpr int LMIN = 2 * NV - 2;
+    const double hh = dmul(0.5, i2d(h));
+    bool amb0, amb1;
+    const int B0 = seg_first_sample(seg_crossing(dsub(hh, 0.5), ec.start[1], ec.inv_step[1]), amb0);
+    const int B1 = seg_first_sample(seg_crossing(hh, ec.start[1], ec.inv_step[1]), amb1);
+    const int start = max(B0, 0), end = min(B1, ec.n);
+    if (start >= min(whi, ec.n)) return false;
+    if (end <= start || start < wlo) return true;
+
+    const int off = start - wlo;                       // samples from `base`
+    const int lo = off & 1;
+    const int hi = lo + (end - start);
+    const uint2* src = reinterpret_cast<const uint2*>(base + (size_t)(off - lo) * 4);
+    uint32_t w[2 * NV];
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+        const uint2 v = src[k];
+        w[2 * k] = v.x;
+        w[2 * k + 1] = v.y;
+    }
+    // carrier phasor of the window's first sample (tracking.py:102), FP64 seed
+    double turns = fma(ec.ca, i2d(start - lo), ec.cb);
+    turns -= drint(turns);
+    float pre, pim;
+    __sincosf((float)turns * 6.283185307179586f, &pim, &pre);
+
+    // samples outside [lo, hi) do not belong to this segment
+    if (hi - lo >= LMIN) {
+        w[0] = lo ? 0u : w[0];
+#pragma unroll
+        for (int u = LMIN; u < 2 * NV; ++u) w[u] = (u < hi) ? w[u] : 0u;
+    } else {                                           // clipped by the epoch's ends
+#pragma unroll
+        for (int u = 0; u < 2 * NV; ++u) w[u] = (u >= lo && u < hi) ? w[u] : 0u;
+    }
+
+    // Y = sum_u x_u w^u: even and odd samples are two Horner chains in w^2, packed in FFMA2
+    const float magic = 12582912.f + 32768.f;
+    const float2 nm = make_float2(-magic, -magic);
+    const float2 w2r = make_float2(ec.w[1][0], ec.w[1][0]);
+    const float2 w2i = make_float2(ec.w[1][1], ec.w[1][1]);
+    const float2 w2n = make_float2(-ec.w[1][1], -ec.w[1][1]);
+    float2 R, I;                                       // (even chain, odd chain) real / imaginary
+#pragma unroll
+    for (int k = NV - 1; k >= 0; --k) {
+        const uint32_t t0 = w[2 * k] ^ 0x80008000u, t1 = w[2 * k + 1] ^ 0x80008000u;
+        float2 xr, xi;
+        xr.x = __uint_as_float(__byte_perm(t0, 0x4B400000u, 0x7610));
+        xr.y = __uint_as_float(__byte_perm(t1, 0x4B400000u, 0x7610));
+        xi.x = __uint_as_float(__byte_perm(t0, 0x4B400000u, 0x7632));
+        xi.y = __uint_as_float(__byte_perm(t1, 0x4B400000u, 0x7632));
+        xr = __fadd2_rn(xr, nm);
+        xi = __fadd2_rn(xi, nm);
+        if (k == NV - 1) {
+            R = xr;
+            I = xi;
+        } else {
+            const float2 r2 = __ffma2_rn(w2n, I, __ffma2_rn(w2r, R, xr));
+            I = __ffma2_rn(w2i, R, __ffma2_rn(w2r, I, xi));
+            R = r2;
+        }
+    }
+    const float w1r = ec.w[0][0], w1i = ec.w[0][1];
+    const float yr = fmaf(-w1i, I.y, fmaf(w1r, R.y, R.x));
+    const float yi = fmaf(w1i, R.y, fmaf(w1r, I.y, I.x));
+    // signal = replica * rfData (tracking.py:105)
+    const float zr = pre * yr - pim * yi, zi = pre * yi + pim * yr;
+    const uint32_t bits = tab[min(max(h, 0), kSegTab - 1)];
+    const float s0 = sign_of_bit(bits & 1u), s1 = sign_of_bit((bits >> 1) & 1u), s2 = sign_of_bit((bits >> 2) & 1u);
+    acc[0] = fmaf(s0, zr, acc[0]); acc[1] = fmaf(s0, zi, acc[1]);
+    acc[2] = fmaf(s1, zr, acc[2]); acc[3] = fmaf(s1, zi, acc[3]);
+    acc[4] = fmaf(s2, zr, acc[4]); acc[5] = fmaf(s2, zi, acc[5]);
+    if (amb0 && B0 >= 0) {                             // first sample needs the exact code indices
+        float pr = pre, pi = pim;
+        if (lo) { pr = pre * w1r - pim * w1i; pi = pre * w1i + pim * w1r; }
+        seg_correct(reinterpret_cast<const uint32_t*>(base)[off], B0, h, pr, pi, &ec, q, cb, acc, &err);
+    }
+    (void)amb1;
+    return true;
+}
+
+// Does the segment path apply to an epoch?  Every code index must stay inside the padded code
+// (no Python wrap-around, no IndexError) and a half chip must last between LMIN and LMIN + 1
+// samples (clear of the integers, so that a segment never exceeds the 2 NV - 1 samples loaded).
+template <int NV>
+__device__ __forceinline__ bool seg_epoch_ok(double start_min, double stop_max, double inv_step) {
+    const double hc = 0.5 * inv_step;
+    return (hc >= (double)(2 * NV - 2) + 0.02) && (hc <= (double)(2 * NV - 1) - 0.02) &&
+           (start_min > -0.999) && (stop_max < (double)(kPaddedChips - 1) - 0.001);
+}
+
 // a / b with a reciprocal rb of b that is correctly rounded or within an ulp: one multiply and
 // the FMA residual correction (Markstein).  Returns the correctly rounded quotient for the
 // operands of this file (checked exhaustively-at-random on the host against IEEE division:
@@ -424,33 +608,61 @@ __device__ __forceinline__ float block_sum8(const float* acc, float (*red)[8]) {
 // ------------------------------------------------------------------------------------------
 // Open-loop batch: one CTA per EPL call (the drop-in EPL() and the teacher-forced parity test).
 // ------------------------------------------------------------------------------------------
+// 8-byte loads per segment of the half-chip path for a kernel instantiation (0 = path not built):
+// int16 IQ with 12-sample chunks (25 MS/s) -> 7, 20-sample chunks (50 MS/s) -> 13, 4-sample
+// chunks (10 MS/s) -> 3.
+template <int DT, int VPC>
+struct SegTraits { static constexpr int NV = 0; };
+template <> struct SegTraits<SYDR_IQ_I16, 1> { static constexpr int NV = 3; };
+template <> struct SegTraits<SYDR_IQ_I16, 3> { static constexpr int NV = 7; };
+template <> struct SegTraits<SYDR_IQ_I16, 5> { static constexpr int NV = 13; };
+
 template <int DT, int VPC>
 __global__ void __launch_bounds__(256) epl_batch_kernel(const uint8_t* __restrict__ iq, long long iq_len,
                                                         double fs, const sydr_epl_args* __restrict__ args,
                                                         const uint32_t* __restrict__ code_bits,
-                                                        double* __restrict__ out) {
+                                                        double* __restrict__ out, int allow_seg) {
     constexpr int SPV = IqTraits<DT>::SPV, BPS = IqTraits<DT>::BPS;
     constexpr int C = SPV * VPC;
+    constexpr int NV = SegTraits<DT, VPC>::NV;
     __shared__ uint32_t cb[kCodeWords];
     __shared__ EpochConst ec_sh;
     __shared__ float red[32][8];
+    __shared__ uint8_t segtab[NV > 0 ? kSegTab : 4];
+    __shared__ int seg_q[3];
     const sydr_epl_args a = args[blockIdx.x];
     if (threadIdx.x < kCodeWords) cb[threadIdx.x] = code_bits[(a.prn - 1) * kCodeWords + threadIdx.x];
-    if (threadIdx.x == 0)
+    const long long a0 = a.start & ~(long long)(SPV - 1);     // 16-byte aligned window start
+    const int lead = (int)(a.start - a0);
+    if (threadIdx.x == 0) {
         make_epoch_const(ec_sh, a.n, fs, a.carrier_freq, a.rem_carrier, a.rem_code, a.code_step, a.spacing, C);
+        ec_sh.seg = 0;
+        if (NV > 0 && allow_seg) {
+            const bool ok = seg_tap_offsets(a.spacing, seg_q);
+            const double smin = fmin(ec_sh.start[0], fmin(ec_sh.start[1], ec_sh.start[2]));
+            const double smax = fmax(ec_sh.start[0], fmax(ec_sh.start[1], ec_sh.start[2]));
+            ec_sh.seg = ok && a.n > 0 && seg_epoch_ok<(NV > 0 ? NV : 1)>(smin, smax + a.code_step * (double)a.n * 1.000001, ec_sh.inv_step[1]);
+            ec_sh.hb = ceil_to_int(2.0 * ec_sh.start[1]) - 1;
+        }
+    }
     __syncthreads();
     if (threadIdx.x < kMaxChunk)
         carrier_table_entry(ec_sh.ca, threadIdx.x, ec_sh.wtab[threadIdx.x][0], ec_sh.wtab[threadIdx.x][1]);
+    if (NV > 0 && ec_sh.seg) build_seg_table(segtab, cb, seg_q);
     __syncthreads();
     const EpochConst& ec = ec_sh;
-    const long long a0 = a.start & ~(long long)(SPV - 1);     // 16-byte aligned window start
-    const int lead = (int)(a.start - a0);
-    const int nchunks = (lead + a.n + C - 1) / C;
     float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     int err = 0;
-    for (int q = threadIdx.x; q < nchunks; q += blockDim.x) {
-        const uint4* src = reinterpret_cast<const uint4*>(iq + (a0 + (long long)q * C) * BPS);
-        correlate_chunk<DT, VPC>(src, q * C - lead, ec, cb, acc, err);
+    if (NV > 0 && ec.seg) {
+        const uint8_t* base = iq + a0 * BPS;
+        for (int h = ec.hb + (int)threadIdx.x;; h += blockDim.x)
+            if (!correlate_segment<(NV > 0 ? NV : 1)>(base, -lead, 0x7fffffff, h, ec, segtab, seg_q, cb, acc, err)) break;
+    } else {
+        const int nchunks = (lead + a.n + C - 1) / C;
+        for (int q = threadIdx.x; q < nchunks; q += blockDim.x) {
+            const uint4* src = reinterpret_cast<const uint4*>(iq + (a0 + (long long)q * C) * BPS);
+            correlate_chunk<DT, VPC>(src, q * C - lead, ec, cb, acc, err);
+        }
     }
     const float tot = block_sum8(acc, red);
     if (threadIdx.x < 6) out[(long long)blockIdx.x * 6 + threadIdx.x] = (double)tot;
@@ -492,6 +704,7 @@ struct TrkParams {
     int use_tma;
     int append;              // records are indexed by the cumulative epoch count
     long long iq_len;        // > 0: overrides the states' iq_len
+    int seg;                 // half-chip segment path allowed (sampling rate fits the instantiation)
     long long* prof;         // optional [n_channels][16] phase cycle counters of thread 0 (NULL = off)
 };
 
@@ -502,6 +715,7 @@ struct EpochCtl {            // published by warps 0 / 1 for every epoch
 };
 
 constexpr int kMaxCluster = 8;
+constexpr int kWinTail = 32;     // samples staged beyond a CTA's window (segments that start inside may end outside)
 constexpr int kTrkMaxThreads = 640;
 
 constexpr int kTrkMaxWarps = kTrkMaxThreads / 32;
@@ -520,6 +734,9 @@ struct TrkShared {           // static shared memory of the closed-loop kernel
     int n_hist[2];           // samples of epoch e (index e & 1), for the carrier warp
     int rec_base;            // index of this call's first record in the channel's output row
     int status;
+    int seg_ok;              // segment path usable for this channel (spacings on the half-chip lattice)
+    int seg_q[3];            // tap offsets in half chips
+    uint8_t segtab[kSegTab]; // code bits of the three taps per lattice index
     long long pc[16];        // diagnostics
     long long tprev, tprev1;
 };
@@ -532,7 +749,7 @@ __device__ __forceinline__ void trk_prefetch(TrkShared& sh, uint8_t* dst, const 
     constexpr int C = SPV * VPC;
     const long long a0 = a & ~(long long)(SPV - 1);
     long long w0 = a0 + (long long)rank * Q * C;
-    long long w1 = w0 + (long long)Q * C;
+    long long w1 = w0 + (long long)Q * C + kWinTail;
     if (w1 > rec_alloc) w1 = rec_alloc & ~(long long)(SPV - 1);
     const long long bytes = (w1 > w0) ? (w1 - w0) * BPS : 0;
     if (bytes > 0) {
@@ -658,7 +875,8 @@ __global__ void __launch_bounds__(kTrkMaxThreads) trk_borre_kernel(const TrkPara
     const int ch = blockIdx.x / S;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, W = blockDim.x >> 5;
     const int Q = P.Q;
-    const uint32_t win_bytes = TMA ? (uint32_t)Q * C * BPS : 0u;
+    constexpr int NV = SegTraits<DT, VPC>::NV;
+    const uint32_t win_bytes = TMA ? (uint32_t)(Q * C + kWinTail) * BPS : 0u;
     const int n_ent = (int)S * W;
 
     sydr_trk_state* gst = P.states + ch;
@@ -677,6 +895,7 @@ __global__ void __launch_bounds__(kTrkMaxThreads) trk_borre_kernel(const TrkPara
         sh.K.dll_c1 = g.dll_tau2 / g.dll_tau1; sh.K.dll_c2 = g.dll_pdi / g.dll_tau1;
         sh.K.pll_c1 = g.pll_tau2 / g.pll_tau1; sh.K.pll_c2 = g.pll_pdi / g.pll_tau1;
         sh.status = sh.cfgs.status;
+        sh.seg_ok = (NV > 0 && P.seg) ? (seg_tap_offsets(sh.cfgs.spacing, sh.seg_q) ? 1 : 0) : 0;
         for (int k = 0; k < 16; ++k) sh.pc[k] = 0;
         mbar_init(&sh.bar_data[0], 1);
         mbar_init(&sh.bar_data[1], 1);
@@ -687,6 +906,10 @@ __global__ void __launch_bounds__(kTrkMaxThreads) trk_borre_kernel(const TrkPara
     }
     __syncthreads();
     if (tid < kCodeWords) sh.cb[tid] = P.code_bits[(sh.cfgs.prn - 1) * kCodeWords + tid];
+    if (NV > 0 && sh.seg_ok) {
+        __syncthreads();
+        build_seg_table(sh.segtab, sh.cb, sh.seg_q);
+    }
     if (S > 1) cluster_sync_all();                  // remote mbarriers are initialised
     const uint8_t* rec_base = P.iq + sh.cfgs.iq_base * BPS;
     const long long rec_alloc = P.iq_alloc - sh.cfgs.iq_base;   // samples readable from rec_base
@@ -727,11 +950,22 @@ __global__ void __launch_bounds__(kTrkMaxThreads) trk_borre_kernel(const TrkPara
                 const double t_stop = dadd(dmul(sc.code_step, dn), t_start);
                 const double t_step = ddiv_by(dsub(t_stop, t_start), dn, sc.inv_n);
                 const int fast = __all_sync(full, sc.inv_step >= (double)(C + 1));   // a chip outlasts a chunk
+                int seg = 0;
+                if (NV > 0) {                                                        // every code index inside the padded code
+                    const bool in = (t_start > -0.999) && (t_stop < (double)(kPaddedChips - 1) - 0.001);
+                    seg = sh.seg_ok && __all_sync(full, in) && seg_epoch_ok<(NV > 0 ? NV : 1)>(0.0, 0.0, sc.inv_step);
+                }
                 SYDR_TICK(8)
                 if (lane < 3) {
                     sh.ctl.ec.start[lane] = t_start;
                     sh.ctl.ec.step[lane] = t_step;
                     sh.ctl.ec.inv_step[lane] = sc.inv_step;                        // ~1/step': estimates only
+                    if (NV > 0 && lane == 1) {                                       // prompt tap: lattice index of this CTA's first sample
+                        const int lead_s = (int)(sc.cur & (long long)(SPV - 1));
+                        const int wlo = max((int)rank * Q * C - lead_s, 0);
+                        sh.ctl.ec.seg = seg;
+                        sh.ctl.ec.hb = ceil_to_int(2.0 * code_phase(wlo, t_start, t_step)) - 1;
+                    }
                 } else if (lane == 3) {
                     sh.ctl.ec.n = sc.n_req;
                     sh.ctl.ec.fast = fast;
@@ -778,16 +1012,25 @@ __global__ void __launch_bounds__(kTrkMaxThreads) trk_borre_kernel(const TrkPara
         int err = 0;
         if (TMA) mbar_wait(&sh.bar_data[buf], (epoch >> 1) & 1);
         SYDR_TICK(2)                                   // wait for the staged window
-        for (int q = tid; q < Q; q += blockDim.x) {
-            const int j0 = (int)(wstart + (long long)q * C) - lead;
-            if (j0 >= n_epoch) break;
-            // ctl.ec is only rewritten after every warp of the cluster has delivered its sums
-            if (TMA) {          // shared-memory window (address space known to the compiler: LDS.128)
-                const uint4* src = reinterpret_cast<const uint4*>(dyn_smem + (size_t)buf * win_bytes + (size_t)q * C * BPS);
-                correlate_chunk<DT, VPC>(src, j0, sh.ctl.ec, sh.cb, acc, err);
-            } else {
-                const uint4* src = reinterpret_cast<const uint4*>(rec_base + (a0 + wstart + (long long)q * C) * BPS);
-                correlate_chunk<DT, VPC>(src, j0, sh.ctl.ec, sh.cb, acc, err);
+        if (NV > 0 && sh.ctl.ec.seg) {
+            // half-chip segments whose first sample lies in this CTA's window
+            const uint8_t* base = TMA ? dyn_smem + (size_t)buf * win_bytes : rec_base + (a0 + wstart) * BPS;
+            const int wlo = (int)wstart - lead;
+            const int whi = (rank == S - 1) ? 0x7fffffff : wlo + Q * C;
+            for (int h = sh.ctl.ec.hb + tid;; h += blockDim.x)
+                if (!correlate_segment<(NV > 0 ? NV : 1)>(base, wlo, whi, h, sh.ctl.ec, sh.segtab, sh.seg_q, sh.cb, acc, err)) break;
+        } else {
+            for (int q = tid; q < Q; q += blockDim.x) {
+                const int j0 = (int)(wstart + (long long)q * C) - lead;
+                if (j0 >= n_epoch) break;
+                // ctl.ec is only rewritten after every warp of the cluster has delivered its sums
+                if (TMA) {          // shared-memory window (address space known to the compiler: LDS.128)
+                    const uint4* src = reinterpret_cast<const uint4*>(dyn_smem + (size_t)buf * win_bytes + (size_t)q * C * BPS);
+                    correlate_chunk<DT, VPC>(src, j0, sh.ctl.ec, sh.cb, acc, err);
+                } else {
+                    const uint4* src = reinterpret_cast<const uint4*>(rec_base + (a0 + wstart + (long long)q * C) * BPS);
+                    correlate_chunk<DT, VPC>(src, j0, sh.ctl.ec, sh.cb, acc, err);
+                }
             }
         }
         SYDR_TICK(3)                                   // correlate (thread 0's chunks)
@@ -855,11 +1098,13 @@ using namespace sydr;
 
 namespace {
 
+int g_trk_mode = 0;                        // 0 = auto, 1 = chunk paths only (sydr_trk_set_mode)
+
 template <int DT, int VPC>
 int launch_epl(const void* d_iq, long long iq_len, double fs, const sydr_epl_args* d_args, int n_calls,
                const uint32_t* bits, double* d_out, cudaStream_t s) {
     epl_batch_kernel<DT, VPC><<<n_calls, 256, 0, s>>>(reinterpret_cast<const uint8_t*>(d_iq), iq_len, fs, d_args,
-                                                 bits, d_out);
+                                                 bits, d_out, g_trk_mode == 0 ? 1 : 0);
     count_launch();
     SYDR_CUDA_CHECK(cudaGetLastError());
     return SYDR_OK;
@@ -868,7 +1113,7 @@ int launch_epl(const void* d_iq, long long iq_len, double fs, const sydr_epl_arg
 template <int DT, int VPC>
 int launch_trk(const TrkParams& P, int n_channels, int cluster, int threads, cudaStream_t s) {
     constexpr int C = IqTraits<DT>::SPV * VPC;
-    const size_t smem = P.use_tma ? (size_t)2 * P.Q * C * IqTraits<DT>::BPS : 0;
+    const size_t smem = P.use_tma ? (size_t)2 * (P.Q * C + kWinTail) * IqTraits<DT>::BPS : 0;
     SYDR_REQUIRE(smem <= 200 * 1024, SYDR_ERR_UNSUPPORTED,
                  "tracking window needs %zu B of shared memory; raise cfg.cluster", smem);
     auto kern = P.use_tma ? trk_borre_kernel<DT, VPC, true> : trk_borre_kernel<DT, VPC, false>;
@@ -926,6 +1171,14 @@ extern "C" {
 // per-phase cycle counts of the loop-closing thread (NULL switches it off).
 int sydr_trk_profile_buffer(long long* d_buf) {
     g_trk_prof = d_buf;
+    return SYDR_OK;
+}
+
+// Diagnostics / tests: 0 = automatic path selection (half-chip segments where they apply),
+// 1 = chunk paths only.
+int sydr_trk_set_mode(int mode) {
+    SYDR_REQUIRE(mode == 0 || mode == 1, SYDR_ERR_ARG, "mode must be 0 or 1");
+    g_trk_mode = mode;
     return SYDR_OK;
 }
 
@@ -987,7 +1240,7 @@ int sydr_trk_run(const void* d_iq, int iq_dtype, long long iq_alloc_samples, dou
     const int vpc = pick_vpc(iq_dtype, fs, gap);
     const int C = spv * vpc;
     // shared-memory budget: two windows of Q*C samples
-    while (use_tma && cluster < 8 && 2 * ((n_max + spv + (long long)C * cluster - 1) / ((long long)C * cluster)) * C * bps > 200 * 1024)
+    while (use_tma && cluster < 8 && 2 * (((n_max + spv + (long long)C * cluster - 1) / ((long long)C * cluster)) * C + kWinTail) * bps > 200 * 1024)
         cluster <<= 1;                                     // (the chunk size chosen above is kept)
     const int Q = (int)((n_max + spv + (long long)C * cluster - 1) / ((long long)C * cluster));
     if (threads <= 0) {
@@ -1010,6 +1263,7 @@ int sydr_trk_run(const void* d_iq, int iq_dtype, long long iq_alloc_samples, dou
     P.use_tma = use_tma;
     P.append = cfg ? (cfg->append != 0) : 0;
     P.iq_len = cfg ? cfg->iq_len : 0;
+    P.seg = (g_trk_mode == 0) ? 1 : 0;
     P.prof = g_trk_prof;
     cudaStream_t s = (cudaStream_t)stream;
     SYDR_DISPATCH_VPC(launch_trk, iq_dtype, vpc, P, n_channels, cluster, threads, s)

@@ -11,6 +11,16 @@ pytestmark = pytest.mark.gpu
 TOL_CORR = 1e-4
 
 
+@pytest.fixture(autouse=True, params=[0, 1], ids=["auto", "chunks"])
+def trk_mode(request):
+    """Every test runs with the automatic path selection (half-chip segments where they apply)
+    and with the chunk formulations only."""
+    from sydr_b200 import _lib as L
+    L.check(L.load().sydr_trk_set_mode(request.param))
+    yield request.param
+    L.check(L.load().sydr_trk_set_mode(0))
+
+
 def corr_err(got, ref):
     ref = np.asarray(ref, dtype=np.float64)
     scale = np.hypot(ref[..., 2], ref[..., 3])
@@ -37,6 +47,36 @@ def test_epl_known_answers(golden):
         for arr in (x.astype(np.complex64), x):
             out2 = epl_batch(to_device_iq(arr), fs, args)
             assert corr_err(out2, cases[:, 10:16]).max() <= TOL_CORR
+
+
+def test_epl_chip_boundaries_on_sample_instants():
+    """Code steps for which chip (and half-chip) boundaries fall exactly on sample instants: the
+    chip of such a sample is decided by the rounding of the reference expression
+    ceil(fl(fl(i*step')+start)) (tracking.py:111-112), which the kernel must reproduce sample for
+    sample (one misplaced sample is ~1e-3 of the prompt magnitude)."""
+    from oracle import sydr_oracle as O
+    from sydr_b200 import _lib as L, synth
+    from sydr_b200.engine import epl_batch, to_device_iq
+    fs = 25e6
+    sc = synth.make_scenario(fs, 16, 0.0035, (3, 7), 77, 250.0)
+    iq = synth.generate_iq(sc)
+    x = synth.to_complex(iq)
+    cases = []
+    for step in (0.04, 0.0390625, 1.0 / 24.5, 0.04 * (1 + 2 ** -40)):
+        for rem in (0.0, 0.5, 0.02, 0.25, 0.04, 1e-12, 0.5 - 1e-13):
+            for start in (0, 3, 1001):
+                cases.append((3, start, 25000, 1234.5, 0.3, rem, step))
+    args = np.zeros(len(cases), dtype=L.EPL_ARGS_DTYPE)
+    for k, c in enumerate(cases):
+        args[k]["prn"], args[k]["start"], args[k]["n"], args[k]["carrier_freq"] = c[0], c[1], c[2], c[3]
+        args[k]["rem_carrier"], args[k]["rem_code"], args[k]["code_step"] = c[4], c[5], c[6]
+        args[k]["spacing"] = (-0.5, 0.0, 0.5)
+    out = epl_batch(to_device_iq(iq), fs, args)
+    code = O.padded_code(3)
+    for k, c in enumerate(cases):
+        ref = O.epl(x[None, c[1]:c[1] + c[2]], code, fs, c[3], c[4], c[5], c[6], [-0.5, 0.0, 0.5])
+        e = corr_err(out[k], np.array(ref))
+        assert e <= 2e-5, (c, e)          # well below one misplaced sample (~1e-3)
 
 
 def test_epl_function_on_reference_fixture(golden):
