@@ -44,6 +44,7 @@ struct EpochConst {
     int fast;              // every tap keeps a chip for more than kMaxChunk samples: <= 1 flip per chunk and tap
     int seg;               // half-chip segment path applies to this epoch (see correlate_segment)
     int hb;                // first half-chip lattice index this CTA looks at
+    int rounds;            // rounds of 32 segments per warp (throughput loop)
 };
 
 __device__ __forceinline__ double dmul(double a, double b) { return __dmul_rn(a, b); }
@@ -356,17 +357,22 @@ __device__ __forceinline__ int seg_first_sample(double x, bool& amb) {
     return __double2loint(xm) + (low ? 0 : 1);
 }
 
-// Signs of the three taps for every lattice index: bit s of tab[H] = padded-code bit of tap s.
-__device__ __forceinline__ void build_seg_table(uint8_t* tab, const uint32_t* cb, const int* q) {
+// Signs of the three taps for every lattice index: byte s of tab[H] is the top byte of +1.0f
+// (0x3F) or -1.0f (0xBF) for tap s, so one PRMT per tap turns the entry into the sign factor.
+__device__ __forceinline__ void build_seg_table(uint32_t* tab, const uint32_t* cb, const int* q) {
     for (int H = threadIdx.x; H < kSegTab; H += blockDim.x) {
-        uint32_t b = 0;
+        uint32_t e = 0;
 #pragma unroll
         for (int s = 0; s < 3; ++s) {
             const int k = min(max((H + q[s] + 1) >> 1, 0), kPaddedChips - 1);
-            b |= ((cb[k >> 5] >> (k & 31)) & 1u) << s;
+            const uint32_t bit = (cb[k >> 5] >> (k & 31)) & 1u;
+            e |= (bit ? 0x3Fu : 0xBFu) << (8 * s);
         }
-        tab[H] = (uint8_t)b;
+        tab[H] = e;
     }
+}
+__device__ __forceinline__ float seg_sign(uint32_t entry, int s) {
+    return __uint_as_float(__byte_perm(entry, 0x00800000u, s == 0 ? 0x0644 : s == 1 ? 0x1644 : 0x2644));
 }
 // q_s = 2 (spacing_s - spacing_prompt) when every spacing is a multiple of half a chip around the
 // prompt tap; returns false otherwise (the chunk paths then serve the channel).
@@ -382,61 +388,53 @@ __device__ __forceinline__ bool seg_tap_offsets(const double* spacing, int* q) {
     return ok;
 }
 
-// Exact treatment of an ambiguous first sample J of segment h (rare): replace the segment's
-// signs by the code values the reference expression gives, tap by tap.
-__device__ __noinline__ void seg_correct(uint32_t raw, int J, int h, float pr, float pi, const EpochConst* ec,
-                                         const int* q, const uint32_t* cb, float* acc, int* err) {
+// Exact treatment of an ambiguous first sample J of segment h (rare): the difference between the
+// code values the reference expression gives and the segment's, tap by tap, times the wiped-off
+// sample.  Returned in registers so that the accumulators never live in local memory.
+struct SegDelta { float d[6]; int err; };
+__device__ __noinline__ SegDelta seg_correct(uint32_t raw, int J, int h, float pr, float pi, const EpochConst* ec,
+                                             const int* q, const uint32_t* cb) {
     const uint32_t t = raw ^ 0x80008000u;
     const float magic = 12582912.f + 32768.f;
     const float xr = __uint_as_float(__byte_perm(t, 0x4B400000u, 0x7610)) - magic;
     const float xi = __uint_as_float(__byte_perm(t, 0x4B400000u, 0x7632)) - magic;
     const float zr = pr * xr - pi * xi, zi = pr * xi + pi * xr;
-    int e = 0;
+    SegDelta o;
+    o.err = 0;
+#pragma unroll
     for (int s = 0; s < 3; ++s) {
         const int k_exact = ceil_to_int(code_phase(J, ec->start[s], ec->step[s]));
         const int k_seg = (h + q[s] + 1) >> 1;
-        if (k_exact == k_seg) continue;
-        const float d = sign_of_bit(chip_bit(cb, k_exact, e)) - sign_of_bit(chip_bit(cb, k_seg, e));
-        acc[2 * s] = fmaf(d, zr, acc[2 * s]);
-        acc[2 * s + 1] = fmaf(d, zi, acc[2 * s + 1]);
+        float d = 0.f;
+        if (k_exact != k_seg) d = sign_of_bit(chip_bit(cb, k_exact, o.err)) - sign_of_bit(chip_bit(cb, k_seg, o.err));
+        o.d[2 * s] = d * zr;
+        o.d[2 * s + 1] = d * zi;
     }
-    if (e) *err = 1;
+    return o;
 }
 
-// One segment of int16 IQ.  `base` points at the sample whose epoch-relative index is `wlo`
-// (8-byte aligned: shared-memory window or global memory); the thread owns segment h if its first
-// sample lies in [wlo, whi).  NV 8-byte loads cover the segment (<= 2 NV - 1 samples from an even
-// address); LMIN = 2 NV - 2 is the shortest unclipped segment of this instantiation.
-// Returns false once the segment starts at or beyond min(whi, n): the caller's loop over h ends.
-template <int NV>
-__device__ __forceinline__ bool correlate_segment(const uint8_t* base, int wlo, int whi, int h, const EpochConst& ec,
-                                                  const uint8_t* tab, const int* q, const uint32_t* cb, float* acc,
-                                                  int& err) {
-    constexpr int LMIN = 2 * NV - 2;
-    const double hh = dmul(0.5, i2d(h));
-    bool amb0, amb1;
-    const int B0 = seg_first_sample(seg_crossing(dsub(hh, 0.5), ec.start[1], ec.inv_step[1]), amb0);
-    const int B1 = seg_first_sample(seg_crossing(hh, ec.start[1], ec.inv_step[1]), amb1);
-    const int start = max(B0, 0), end = min(B1, ec.n);
-    if (start >= min(whi, ec.n)) return false;
-    if (end <= start || start < wlo) return true;
+// First sample of segment h+1 (see above); amb = it needs the exact evaluation.
+__device__ __forceinline__ int seg_bound(int h, const EpochConst& ec, bool& amb) {
+    return seg_first_sample(seg_crossing(dmul(0.5, i2d(h)), ec.start[1], ec.inv_step[1]), amb);
+}
 
-    const int off = start - wlo;                       // samples from `base`
-    const int lo = off & 1;
-    const int hi = lo + (end - start);
-    const uint2* src = reinterpret_cast<const uint2*>(base + (size_t)(off - lo) * 4);
-    uint32_t w[2 * NV];
-#pragma unroll
-    for (int k = 0; k < NV; ++k) {
-        const uint2 v = src[k];
-        w[2 * k] = v.x;
-        w[2 * k + 1] = v.y;
-    }
-    // carrier phasor of the window's first sample (tracking.py:102), FP64 seed
-    double turns = fma(ec.ca, i2d(start - lo), ec.cb);
+// Carrier phasor of epoch-relative sample j (tracking.py:102), FP64 seed.
+__device__ __forceinline__ void seg_phasor(const EpochConst& ec, int j, float& pre, float& pim) {
+    double turns = fma(ec.ca, i2d(j), ec.cb);
     turns -= drint(turns);
-    float pre, pim;
     __sincosf((float)turns * 6.283185307179586f, &pim, &pre);
+}
+
+// The arithmetic of one segment of int16 IQ.  w[0 .. 2NV) are the raw samples from the even
+// address at or below the segment's first sample; samples [lo, hi) of them belong to the segment;
+// (pre, pim) = carrier phasor of w[0], whose epoch-relative index is j0.  LMIN = 2 NV - 2 is the
+// shortest unclipped segment.  CLAMP: h may lie outside the sign table (general kernel only).
+template <int NV, bool CLAMP>
+__device__ __forceinline__ void seg_body(uint32_t* w, int lo, int hi, int j0, float pre, float pim, int h, bool amb0,
+                                         const EpochConst& ec, const uint32_t* tab, const int* q, const uint32_t* cb,
+                                         float* acc, int& err) {
+    constexpr int LMIN = 2 * NV - 2;
+    const uint32_t raw_first = lo ? w[1] : w[0];       // for the exact evaluation of an ambiguous first sample
 
     // samples outside [lo, hi) do not belong to this segment
     if (hi - lo >= LMIN) {
@@ -448,13 +446,15 @@ __device__ __forceinline__ bool correlate_segment(const uint8_t* base, int wlo, 
         for (int u = 0; u < 2 * NV; ++u) w[u] = (u >= lo && u < hi) ? w[u] : 0u;
     }
 
-    // Y = sum_u x_u w^u: even and odd samples are two Horner chains in w^2, packed in FFMA2
+    // Y = sum_u x_u w^u.  Samples u = 4m, 4m+1 (pairs k = 2m) and u = 4m+2, 4m+3 (pairs k = 2m+1)
+    // form two sets of Horner chains in w^4; each set packs its even / odd sample chain in FFMA2.
+    // Four independent chains halve the dependent depth; the sets are joined with one rotation by w^2.
     const float magic = 12582912.f + 32768.f;
     const float2 nm = make_float2(-magic, -magic);
-    const float2 w2r = make_float2(ec.w[1][0], ec.w[1][0]);
-    const float2 w2i = make_float2(ec.w[1][1], ec.w[1][1]);
-    const float2 w2n = make_float2(-ec.w[1][1], -ec.w[1][1]);
-    float2 R, I;                                       // (even chain, odd chain) real / imaginary
+    const float2 w4r = make_float2(ec.w[3][0], ec.w[3][0]);
+    const float2 w4i = make_float2(ec.w[3][1], ec.w[3][1]);
+    const float2 w4n = make_float2(-ec.w[3][1], -ec.w[3][1]);
+    float2 RA = make_float2(0.f, 0.f), IA = RA, RB = RA, IB = RA;   // (even sample, odd sample) of set A / B
 #pragma unroll
     for (int k = NV - 1; k >= 0; --k) {
         const uint32_t t0 = w[2 * k] ^ 0x80008000u, t1 = w[2 * k + 1] ^ 0x80008000u;
@@ -465,32 +465,172 @@ __device__ __forceinline__ bool correlate_segment(const uint8_t* base, int wlo, 
         xi.y = __uint_as_float(__byte_perm(t1, 0x4B400000u, 0x7632));
         xr = __fadd2_rn(xr, nm);
         xi = __fadd2_rn(xi, nm);
-        if (k == NV - 1) {
-            R = xr;
-            I = xi;
+        float2& R_ = (k & 1) ? RB : RA;
+        float2& I_ = (k & 1) ? IB : IA;
+        if (k >= NV - 2) {                               // first pair of its set
+            R_ = xr;
+            I_ = xi;
         } else {
-            const float2 r2 = __ffma2_rn(w2n, I, __ffma2_rn(w2r, R, xr));
-            I = __ffma2_rn(w2i, R, __ffma2_rn(w2r, I, xi));
-            R = r2;
+            const float2 r2 = __ffma2_rn(w4n, I_, __ffma2_rn(w4r, R_, xr));
+            I_ = __ffma2_rn(w4i, R_, __ffma2_rn(w4r, I_, xi));
+            R_ = r2;
         }
+    }
+    float2 R = RA, I = IA;
+    if (NV > 1) {                                        // set B starts two samples later
+        const float2 w2r = make_float2(ec.w[1][0], ec.w[1][0]);
+        const float2 w2i = make_float2(ec.w[1][1], ec.w[1][1]);
+        const float2 w2n = make_float2(-ec.w[1][1], -ec.w[1][1]);
+        R = __ffma2_rn(w2n, IB, __ffma2_rn(w2r, RB, RA));
+        I = __ffma2_rn(w2i, RB, __ffma2_rn(w2r, IB, IA));
     }
     const float w1r = ec.w[0][0], w1i = ec.w[0][1];
     const float yr = fmaf(-w1i, I.y, fmaf(w1r, R.y, R.x));
     const float yi = fmaf(w1i, R.y, fmaf(w1r, I.y, I.x));
     // signal = replica * rfData (tracking.py:105)
     const float zr = pre * yr - pim * yi, zi = pre * yi + pim * yr;
-    const uint32_t bits = tab[min(max(h, 0), kSegTab - 1)];
-    const float s0 = sign_of_bit(bits & 1u), s1 = sign_of_bit((bits >> 1) & 1u), s2 = sign_of_bit((bits >> 2) & 1u);
+    const uint32_t e = tab[CLAMP ? min(max(h, 0), kSegTab - 1) : h];
+    const float s0 = seg_sign(e, 0), s1 = seg_sign(e, 1), s2 = seg_sign(e, 2);
     acc[0] = fmaf(s0, zr, acc[0]); acc[1] = fmaf(s0, zi, acc[1]);
     acc[2] = fmaf(s1, zr, acc[2]); acc[3] = fmaf(s1, zi, acc[3]);
     acc[4] = fmaf(s2, zr, acc[4]); acc[5] = fmaf(s2, zi, acc[5]);
-    if (amb0 && B0 >= 0) {                             // first sample needs the exact code indices
+    if (amb0) {                                        // first sample needs the exact code indices
         float pr = pre, pi = pim;
         if (lo) { pr = pre * w1r - pim * w1i; pi = pre * w1i + pim * w1r; }
-        seg_correct(reinterpret_cast<const uint32_t*>(base)[off], B0, h, pr, pi, &ec, q, cb, acc, &err);
+        const SegDelta dlt = seg_correct(raw_first, j0 + lo, h, pr, pi, &ec, q, cb);
+#pragma unroll
+        for (int k = 0; k < 6; ++k) acc[k] += dlt.d[k];
+        err |= dlt.err;
     }
-    (void)amb1;
+}
+
+// One segment from a window in shared or global memory.  `base` points at the sample whose
+// epoch-relative index is `wlo` (8-byte aligned); the thread owns segment h if its first sample
+// lies in [wlo, whi).  Returns false once the segment starts at or beyond min(whi, n): the
+// caller's loop over h ends.
+template <int NV>
+__device__ __forceinline__ bool correlate_segment(const uint8_t* base, int wlo, int whi, int h, const EpochConst& ec,
+                                                  const uint32_t* tab, const int* q, const uint32_t* cb, float* acc,
+                                                  int& err) {
+    bool amb0, amb1;
+    const int B0 = seg_bound(h - 1, ec, amb0);
+    const int B1 = seg_bound(h, ec, amb1);
+    const int start = max(B0, 0), end = min(B1, ec.n);
+    if (start >= min(whi, ec.n)) return false;
+    if (end <= start || start < wlo) return true;
+    const int off = start - wlo;                       // samples from `base`
+    const int lo = off & 1;
+    const uint2* src = reinterpret_cast<const uint2*>(base + (size_t)(off - lo) * 4);
+    uint32_t w[2 * NV];
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+        const uint2 v = src[k];
+        w[2 * k] = v.x;
+        w[2 * k + 1] = v.y;
+    }
+    float pre, pim;
+    seg_phasor(ec, start - lo, pre, pim);
+    seg_body<NV, true>(w, lo, lo + (end - start), start - lo, pre, pim, h, amb0 && B0 >= 0, ec, tab, q, cb, acc, err);
     return true;
+}
+
+// ---- throughput loop: every warp owns R*32 consecutive segments and walks them in R rounds of
+// 32.  The samples of the *next* round (one contiguous piece of the recording, ~1.6 KB) travel
+// into a private shared-memory slot of the warp with one TMA bulk copy (cp.async.bulk + mbarrier,
+// no LSU work) while the current round is computed, and the first sample of segment h+1 is
+// taken from the neighbouring lane instead of being located twice.
+template <int NV>
+struct RoundTraits {
+    // a lane's windows of consecutive rounds start 32 segments apart: 32 (2 NV - 2) - 1 ..
+    // 32 (2 NV - 1) + 1 samples; the carrier rotations by these distances are tabulated per epoch
+    static constexpr int kRotBase = 32 * (2 * NV - 2) - 1;
+    static constexpr int kRotN = 35;
+};
+constexpr int kRotMax = 36;
+
+__device__ __forceinline__ void ldg64_nc(const void* p, uint32_t& a, uint32_t& b) {
+    asm volatile("ld.global.nc.v2.u32 {%0, %1}, [%2];" : "=r"(a), "=r"(b) : "l"(p));
+}
+
+// Throughput loop: every warp owns R*32 consecutive segments and walks them in R rounds of 32.
+// The 2 NV words of a lane's *next* segment are requested from global memory (L1 / L2: the 12
+// channels of a recording read the same lines) before the current segment is computed, so their
+// latency hides behind ~200 instructions; the boundary behind a lane's segment comes from the
+// neighbouring lane, the boundary in front of its next segment from one FP64 addition, and the
+// carrier phasor from a tabulated rotation of the previous round's.
+template <int NV>
+__device__ __forceinline__ void correlate_rounds(const uint8_t* rec_epoch /* sample 0 of the epoch */, int rounds,
+                                                 const EpochConst& ec, const float2* rot, const uint32_t* tab,
+                                                 const int* q, const uint32_t* cb, float* acc, int& err) {
+    using RT = RoundTraits<NV>;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned full = 0xffffffffu;
+    const int n = ec.n;
+    // parity of the epoch's first sample inside its 8-byte pair
+    const int al = (int)((reinterpret_cast<uintptr_t>(rec_epoch) >> 2) & 1);
+    const int h0 = ec.hb + warp * rounds * 32;              // first segment of the warp
+    int h = h0 + lane;
+    // crossing of the lattice point in front of this lane's segment; advanced by 32 half chips per
+    // round (x is only an estimate: seg_first_sample flags the cases that need the exact expression)
+    const double start_b = ec.start[1], inv_step = ec.inv_step[1];
+    double x = seg_crossing(dmul(0.5, i2d(h - 1)), start_b, inv_step);
+    const double d32 = 16.0 * inv_step;
+    bool ambc;
+    int Bc = seg_first_sample(x, ambc);
+    // the boundary behind the warp's last segment, evaluated like the next warp's first
+    bool amb_unused;
+    const int Bend = seg_first_sample(seg_crossing(dmul(0.5, i2d(h0 + rounds * 32 - 1)), start_b, inv_step), amb_unused);
+    float pre = 1.f, pim = 0.f;
+    int jprev = -0x40000000;                                // forces the FP64 seed in the first round
+    uint32_t wa[2 * NV], wb[2 * NV];
+    auto request = [&](int B, uint32_t* w) {                // the 2 NV words from the even address at the segment's start
+        const int s0 = min(max(B, 0), n);
+        const uint8_t* g = rec_epoch + (long long)(s0 - ((s0 + al) & 1)) * 4;
+#pragma unroll
+        for (int k = 0; k < NV; ++k) ldg64_nc(g + 8 * k, w[2 * k], w[2 * k + 1]);
+    };
+    request(Bc, wa);
+
+#define SYDR_ROUND(WCUR, WNXT)                                                                             \
+    {                                                                                                      \
+        const double xn = x + d32;                                                                         \
+        bool ambn;                                                                                         \
+        const int Bn = seg_first_sample(xn, ambn);                                                         \
+        int B1 = __shfl_down_sync(full, Bc, 1);                                                            \
+        const int Bw = __shfl_sync(full, Bn, 0);                                                           \
+        if (lane == 31) B1 = (r + 1 == rounds) ? Bend : Bw;                                                \
+        const int start = max(Bc, 0), end = min(B1, n);                                                    \
+        if (__all_sync(full, start >= n)) break;                                                           \
+        if (r + 1 < rounds) request(Bn, WNXT);                                                             \
+        if (end > start) {                                                                                 \
+            const int lo = (start + al) & 1;                                                               \
+            const int j0 = start - lo;                                                                     \
+            const uint32_t d = (uint32_t)(j0 - jprev - RT::kRotBase);                                      \
+            if (d < (uint32_t)RT::kRotN) {                                                                 \
+                const float2 c = rot[d];                                                                   \
+                const float t = pre * c.x - pim * c.y;                                                     \
+                pim = pre * c.y + pim * c.x;                                                               \
+                pre = t;                                                                                   \
+            } else {                                                                                       \
+                seg_phasor(ec, j0, pre, pim);                                                              \
+            }                                                                                              \
+            jprev = j0;                                                                                    \
+            seg_body<NV, false>(WCUR, lo, lo + (end - start), j0, pre, pim, h, ambc && Bc >= 0, ec, tab,   \
+                                q, cb, acc, err);                                                          \
+        }                                                                                                  \
+        x = xn;                                                                                            \
+        Bc = Bn;                                                                                           \
+        ambc = ambn;                                                                                       \
+        h += 32;                                                                                           \
+        ++r;                                                                                               \
+    }
+
+    for (int r = 0; r < rounds;) {
+        SYDR_ROUND(wa, wb)
+        if (r >= rounds) break;
+        SYDR_ROUND(wb, wa)
+    }
+#undef SYDR_ROUND
 }
 
 // Does the segment path apply to an epoch?  Every code index must stay inside the padded code
@@ -628,7 +768,7 @@ __global__ void __launch_bounds__(256) epl_batch_kernel(const uint8_t* __restric
     __shared__ uint32_t cb[kCodeWords];
     __shared__ EpochConst ec_sh;
     __shared__ float red[32][8];
-    __shared__ uint8_t segtab[NV > 0 ? kSegTab : 4];
+    __shared__ uint32_t segtab[NV > 0 ? kSegTab : 4];
     __shared__ int seg_q[3];
     const sydr_epl_args a = args[blockIdx.x];
     if (threadIdx.x < kCodeWords) cb[threadIdx.x] = code_bits[(a.prn - 1) * kCodeWords + threadIdx.x];
@@ -705,6 +845,7 @@ struct TrkParams {
     int append;              // records are indexed by the cumulative epoch count
     long long iq_len;        // > 0: overrides the states' iq_len
     int seg;                 // half-chip segment path allowed (sampling rate fits the instantiation)
+    int resume;              // follow-up of a LEAN launch: continue the record rows, serve kNeedGeneral channels
     long long* prof;         // optional [n_channels][16] phase cycle counters of thread 0 (NULL = off)
 };
 
@@ -717,16 +858,20 @@ struct EpochCtl {            // published by warps 0 / 1 for every epoch
 constexpr int kMaxCluster = 8;
 constexpr int kWinTail = 32;     // samples staged beyond a CTA's window (segments that start inside may end outside)
 constexpr int kTrkMaxThreads = 640;
+constexpr int kLeanThreads = 256;
+constexpr int kNeedGeneral = 2;  // channel status: stopped in front of an epoch only the general kernel serves
 
 constexpr int kTrkMaxWarps = kTrkMaxThreads / 32;
 
-struct TrkShared {           // static shared memory of the closed-loop kernel
+template <int NE, int NTAB>
+struct TrkSharedT {          // static shared memory of the closed-loop kernel
     uint32_t cb[kCodeWords];
     EpochCtl ctl;
     // per-warp partial sums of every CTA of the cluster, [slot][rank * W + warp][component]
-    alignas(16) double gather[2][kMaxCluster * kTrkMaxWarps][8];
+    alignas(16) double gather[2][NE][8];
     alignas(8) uint64_t bar_data[2];
     uint64_t bar_gather[2];
+    float2 rot[kRotMax];     // throughput loop: carrier rotation between a lane's consecutive windows
     sydr_trk_state cfgs;     // the channel's state as loaded (constants live here)
     CodeState sc;            // owned by warp 0
     CarrierState sk;         // owned by warp 1
@@ -736,14 +881,14 @@ struct TrkShared {           // static shared memory of the closed-loop kernel
     int status;
     int seg_ok;              // segment path usable for this channel (spacings on the half-chip lattice)
     int seg_q[3];            // tap offsets in half chips
-    uint8_t segtab[kSegTab]; // code bits of the three taps per lattice index
+    uint32_t segtab[NTAB];   // sign bytes of the three taps per lattice index
     long long pc[16];        // diagnostics
     long long tprev, tprev1;
 };
 
 // TMA bulk copy of one CTA's window of the epoch starting at sample `a` (executed by one lane).
-template <int DT, int VPC>
-__device__ __forceinline__ void trk_prefetch(TrkShared& sh, uint8_t* dst, const uint8_t* rec_base, long long rec_alloc,
+template <int DT, int VPC, class SH>
+__device__ __forceinline__ void trk_prefetch(SH& sh, uint8_t* dst, const uint8_t* rec_base, long long rec_alloc,
                                              long long a, uint32_t rank, int Q, int buf) {
     constexpr int SPV = IqTraits<DT>::SPV, BPS = IqTraits<DT>::BPS;
     constexpr int C = SPV * VPC;
@@ -770,7 +915,8 @@ __device__ __forceinline__ void trk_prefetch(TrkShared& sh, uint8_t* dst, const 
 // Lane L adds the entries i = (L >> 3) mod 4 of component L & 7 in a fixed order (identical in
 // every CTA, so the redundant loop closures agree bit for bit); on return every lane holds the
 // total of component L & 7.
-__device__ __forceinline__ double gather_total(const TrkShared& sh, int slot, int n_ent, int lane) {
+template <class SH>
+__device__ __forceinline__ double gather_total(const SH& sh, int slot, int n_ent, int lane) {
     const int c = lane & 7;
     const double* g = &sh.gather[slot][0][c];
     double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
@@ -787,7 +933,8 @@ __device__ __forceinline__ double gather_total(const TrkShared& sh, int slot, in
 
 // Warp 0: close the CODE loop of epoch e (DLL_NNEML + Borre filter + code NCO,
 // channel_l1ca_borre.py:383-388, 422-429), store its share of the epoch record.
-__device__ __forceinline__ void code_close(TrkShared& sh, CodeState& st, int& status, double ck, sydr_trk_epoch* rec,
+template <class SH>
+__device__ __forceinline__ void code_close(SH& sh, CodeState& st, int& status, double ck, sydr_trk_epoch* rec,
                                            int lane) {
     const unsigned full = 0xffffffffu;
     // |E| (even lanes) and |L| (odd lanes)                                    tracking.py:126
@@ -823,7 +970,8 @@ __device__ __forceinline__ void code_close(TrkShared& sh, CodeState& st, int& st
 
 // Warp 1: close the CARRIER loop of epoch e (remaining carrier phase, PLL_costa + Borre filter +
 // carrier NCO, channel_l1ca_borre.py:364-365, 391-396, 423), store its share of the record.
-__device__ __forceinline__ void carrier_close(TrkShared& sh, CarrierState& st, double ck, int n_epoch,
+template <class SH>
+__device__ __forceinline__ void carrier_close(SH& sh, CarrierState& st, double ck, int n_epoch,
                                               sydr_trk_epoch* rec, int lane) {
     const unsigned full = 0xffffffffu;
     const double ip = __shfl_sync(full, ck, 2), qp = __shfl_sync(full, ck, 3);
@@ -862,12 +1010,17 @@ __device__ __forceinline__ void carrier_close(TrkShared& sh, CarrierState& st, d
 //       loop in FP64, store the epoch record and publish the constants of the next epoch.
 // The TMA window of the next epoch is requested right after (A) by the last warp, off the
 // loop-closing path.
-template <int DT, int VPC, bool TMA>
-__global__ void __launch_bounds__(kTrkMaxThreads) trk_borre_kernel(const TrkParams P) {
+// LEAN = throughput instantiation: segment path only, <= 256 threads and <= 80 registers so that
+// three channels share an SM and one channel's loop closure hides behind the others' correlation.
+// An epoch the segment path cannot serve stops the channel with status kNeedGeneral; the host
+// then repeats the launch with the general instantiation (sydr_trk_run).
+template <int DT, int VPC, bool TMA, bool LEAN>
+__global__ void __launch_bounds__(LEAN ? kLeanThreads : kTrkMaxThreads, LEAN ? 3 : 1) trk_borre_kernel(const TrkParams P) {
     constexpr int SPV = IqTraits<DT>::SPV, BPS = IqTraits<DT>::BPS;
     constexpr int C = SPV * VPC;
     extern __shared__ __align__(128) uint8_t dyn_smem[];
-    __shared__ __align__(16) TrkShared sh;
+    constexpr int NV = SegTraits<DT, VPC>::NV;
+    __shared__ __align__(16) TrkSharedT<(LEAN ? kLeanThreads / 32 : kMaxCluster * kTrkMaxWarps), (NV > 0 ? kSegTab : 1)> sh;
     const unsigned full = 0xffffffffu;
 
     const uint32_t S = cluster_nctarank();
@@ -875,7 +1028,6 @@ __global__ void __launch_bounds__(kTrkMaxThreads) trk_borre_kernel(const TrkPara
     const int ch = blockIdx.x / S;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, W = blockDim.x >> 5;
     const int Q = P.Q;
-    constexpr int NV = SegTraits<DT, VPC>::NV;
     const uint32_t win_bytes = TMA ? (uint32_t)(Q * C + kWinTail) * BPS : 0u;
     const int n_ent = (int)S * W;
 
@@ -883,7 +1035,8 @@ __global__ void __launch_bounds__(kTrkMaxThreads) trk_borre_kernel(const TrkPara
     if (tid == 0) {
         sh.cfgs = *gst;
         if (P.iq_len > 0) sh.cfgs.iq_len = P.iq_len;
-        sh.rec_base = P.append ? (int)sh.cfgs.epochs_done : 0;
+        sh.rec_base = P.append ? (int)sh.cfgs.epochs_done : (P.resume ? P.nepochs[ch] : 0);
+        if (P.resume && sh.cfgs.status == kNeedGeneral) sh.cfgs.status = 0;
         const sydr_trk_state& g = sh.cfgs;
         sh.sc.cur = g.cur; sh.sc.n_req = (int)g.n_req;
         sh.sc.code_freq = g.code_freq; sh.sc.code_step = g.code_step; sh.sc.rem_code = g.rem_code;
@@ -941,20 +1094,27 @@ __global__ void __launch_bounds__(kTrkMaxThreads) trk_borre_kernel(const TrkPara
         // ---- (C, second half) publish the constants of epoch `epoch`
         if (warp == 0) {
             if (sc.n_req <= 0 || (long long)sc.n_req + SPV > (long long)S * Q * C) status = SYDR_ERR_STATE;
-            const bool stop = (status != 0) || (sh.rec_base + epoch >= P.max_epochs) || (sc.cur + sc.n_req > sh.cfgs.iq_len);
+            bool stop = (status != 0) || (sh.rec_base + epoch >= P.max_epochs) || (sc.cur + sc.n_req > sh.cfgs.iq_len);
+            double t_start = 0.0, t_step = 0.0, t_stop = 0.0;
+            int fast = 0, seg = 0;
             if (!stop) {
                 // tap constants (numpy linspace arithmetic, tracking.py:110-112), lane s < 3 = correlator s
                 const double dn = i2d(sc.n_req);
                 sc.inv_n = newton_rcp(dn, newton_rcp(dn, sc.inv_n));                  // n moves by +-1 at most
-                const double t_start = dadd(sc.rem_code, sh.cfgs.spacing[min(lane, 2)]);
-                const double t_stop = dadd(dmul(sc.code_step, dn), t_start);
-                const double t_step = ddiv_by(dsub(t_stop, t_start), dn, sc.inv_n);
-                const int fast = __all_sync(full, sc.inv_step >= (double)(C + 1));   // a chip outlasts a chunk
-                int seg = 0;
+                t_start = dadd(sc.rem_code, sh.cfgs.spacing[min(lane, 2)]);
+                t_stop = dadd(dmul(sc.code_step, dn), t_start);
+                t_step = ddiv_by(dsub(t_stop, t_start), dn, sc.inv_n);
+                fast = __all_sync(full, sc.inv_step >= (double)(C + 1));             // a chip outlasts a chunk
                 if (NV > 0) {                                                        // every code index inside the padded code
                     const bool in = (t_start > -0.999) && (t_stop < (double)(kPaddedChips - 1) - 0.001);
                     seg = sh.seg_ok && __all_sync(full, in) && seg_epoch_ok<(NV > 0 ? NV : 1)>(0.0, 0.0, sc.inv_step);
                 }
+                if (LEAN && !seg) {                                                  // leave this epoch to the general kernel
+                    stop = true;
+                    status = kNeedGeneral;
+                }
+            }
+            if (!stop) {
                 SYDR_TICK(8)
                 if (lane < 3) {
                     sh.ctl.ec.start[lane] = t_start;
@@ -963,8 +1123,11 @@ __global__ void __launch_bounds__(kTrkMaxThreads) trk_borre_kernel(const TrkPara
                     if (NV > 0 && lane == 1) {                                       // prompt tap: lattice index of this CTA's first sample
                         const int lead_s = (int)(sc.cur & (long long)(SPV - 1));
                         const int wlo = max((int)rank * Q * C - lead_s, 0);
+                        const int hb = ceil_to_int(2.0 * code_phase(wlo, t_start, t_step)) - 1;
                         sh.ctl.ec.seg = seg;
-                        sh.ctl.ec.hb = ceil_to_int(2.0 * code_phase(wlo, t_start, t_step)) - 1;
+                        sh.ctl.ec.hb = hb;
+                        // segments hb .. ceil(2 phase(n)) cover the epoch; W warps take 32 per round
+                        sh.ctl.ec.rounds = (ceil_to_int(2.0 * t_stop) - hb + 32 * W) / (32 * W);
                     }
                 } else if (lane == 3) {
                     sh.ctl.ec.n = sc.n_req;
@@ -987,7 +1150,13 @@ __global__ void __launch_bounds__(kTrkMaxThreads) trk_borre_kernel(const TrkPara
                 sh.ctl.ec.w[lane - 1][0] = w[lane - 1][0];
                 sh.ctl.ec.w[lane - 1][1] = w[lane - 1][1];
             }
-            if (lane < kMaxChunk) carrier_table_entry(ca, lane, sh.ctl.ec.wtab[lane][0], sh.ctl.ec.wtab[lane][1]);
+            if (LEAN) {
+                constexpr int RB = RoundTraits<(NV > 0 ? NV : 1)>::kRotBase;
+                carrier_table_entry(ca, RB + lane, sh.rot[lane].x, sh.rot[lane].y);
+                if (lane < kRotMax - 32) carrier_table_entry(ca, RB + 32 + lane, sh.rot[32 + lane].x, sh.rot[32 + lane].y);
+            } else if (lane < kMaxChunk) {
+                carrier_table_entry(ca, lane, sh.ctl.ec.wtab[lane][0], sh.ctl.ec.wtab[lane][1]);
+            }
             SYDR_TICK1(13)                             // carrier warp: constants of the next epoch
         }
         SYDR_TICK(0)                                   // epoch constants
@@ -1012,14 +1181,17 @@ __global__ void __launch_bounds__(kTrkMaxThreads) trk_borre_kernel(const TrkPara
         int err = 0;
         if (TMA) mbar_wait(&sh.bar_data[buf], (epoch >> 1) & 1);
         SYDR_TICK(2)                                   // wait for the staged window
-        if (NV > 0 && sh.ctl.ec.seg) {
+        if (NV > 0 && LEAN) {
+            correlate_rounds<(NV > 0 ? NV : 1)>(rec_base + a * BPS, sh.ctl.ec.rounds, sh.ctl.ec, sh.rot, sh.segtab, sh.seg_q,
+                                                sh.cb, acc, err);
+        } else if (NV > 0 && sh.ctl.ec.seg) {
             // half-chip segments whose first sample lies in this CTA's window
             const uint8_t* base = TMA ? dyn_smem + (size_t)buf * win_bytes : rec_base + (a0 + wstart) * BPS;
             const int wlo = (int)wstart - lead;
             const int whi = (rank == S - 1) ? 0x7fffffff : wlo + Q * C;
             for (int h = sh.ctl.ec.hb + tid;; h += blockDim.x)
                 if (!correlate_segment<(NV > 0 ? NV : 1)>(base, wlo, whi, h, sh.ctl.ec, sh.segtab, sh.seg_q, sh.cb, acc, err)) break;
-        } else {
+        } else if (!LEAN) {
             for (int q = tid; q < Q; q += blockDim.x) {
                 const int j0 = (int)(wstart + (long long)q * C) - lead;
                 if (j0 >= n_epoch) break;
@@ -1111,17 +1283,25 @@ int launch_epl(const void* d_iq, long long iq_len, double fs, const sydr_epl_arg
 }
 
 template <int DT, int VPC>
-int launch_trk(const TrkParams& P, int n_channels, int cluster, int threads, cudaStream_t s) {
+int launch_trk(const TrkParams& P, int n_channels, int cluster, int threads, int lean, cudaStream_t s) {
     constexpr int C = IqTraits<DT>::SPV * VPC;
     const size_t smem = P.use_tma ? (size_t)2 * (P.Q * C + kWinTail) * IqTraits<DT>::BPS : 0;
     SYDR_REQUIRE(smem <= 200 * 1024, SYDR_ERR_UNSUPPORTED,
                  "tracking window needs %zu B of shared memory; raise cfg.cluster", smem);
-    auto kern = P.use_tma ? trk_borre_kernel<DT, VPC, true> : trk_borre_kernel<DT, VPC, false>;
-    SYDR_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    constexpr bool HAS_LEAN = SegTraits<DT, VPC>::NV > 0;
+    auto kern = P.use_tma ? trk_borre_kernel<DT, VPC, true, false> : trk_borre_kernel<DT, VPC, false, false>;
+    size_t smem_launch = smem;
+    if constexpr (HAS_LEAN) {
+        if (lean) {
+            kern = trk_borre_kernel<DT, VPC, false, true>;
+            smem_launch = 0;                                    // the throughput loop reads global memory directly
+        }
+    }
+    SYDR_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_launch));
     cudaLaunchConfig_t lc = {};
     lc.gridDim = dim3((unsigned)(n_channels * cluster));
     lc.blockDim = dim3((unsigned)threads);
-    lc.dynamicSmemBytes = smem;
+    lc.dynamicSmemBytes = smem_launch;
     lc.stream = s;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeClusterDimension;
@@ -1162,6 +1342,13 @@ static int pick_vpc(int iq_dtype, double fs, double gap) {
         case SYDR_IQ_F32 * 16 + 10: return FN<SYDR_IQ_F32, 10>(__VA_ARGS__);           \
         default: break;                                                                \
     }
+
+static int dispatch_trk(int iq_dtype, int vpc, const TrkParams& P, int n_channels, int cluster, int threads, int lean,
+                        cudaStream_t s) {
+    SYDR_DISPATCH_VPC(launch_trk, iq_dtype, vpc, P, n_channels, cluster, threads, lean, s)
+    set_error("sydr_trk_run: no kernel for this chunk size");
+    return SYDR_ERR_UNSUPPORTED;
+}
 
 static long long* g_trk_prof = nullptr;    // set by sydr_trk_profile_buffer (diagnostics)
 
@@ -1250,6 +1437,18 @@ int sydr_trk_run(const void* d_iq, int iq_dtype, long long iq_alloc_samples, dou
     }
     SYDR_REQUIRE(threads % 32 == 0 && threads >= 64 && threads <= kTrkMaxThreads, SYDR_ERR_ARG, "threads must be a multiple of 32 in [64, %d] (got %d)", kTrkMaxThreads, threads);
 
+    // Throughput instantiation (LEAN): int16 IQ whose half chip fits the segment path, one CTA of
+    // <= 256 threads per channel reading global memory directly, four CTAs per SM.  Chosen
+    // automatically when the channels outnumber the SMs' latency-mode capacity, or explicitly
+    // with cluster = 1, use_tma = 0 and threads <= 256.
+    int nv = 0;
+    if (iq_dtype == SYDR_IQ_I16) nv = (vpc == 1) ? 3 : (vpc == 3) ? 7 : (vpc == 5) ? 13 : 0;
+    const double half_chip = 0.5 * fs / kCodeFreq;
+    const bool seg_fits = nv > 0 && g_trk_mode == 0 && half_chip >= 2 * nv - 2 + 0.05 && half_chip <= 2 * nv - 1 - 0.05;
+    const bool auto_shape = !cfg || cfg->cluster <= 0;
+    const bool lean = seg_fits && ((auto_shape && cluster == 1) ||
+                                   (!auto_shape && cluster == 1 && !use_tma && threads > 0 && threads <= kLeanThreads));
+
     TrkParams P;
     P.iq = reinterpret_cast<const uint8_t*>(d_iq);
     P.iq_alloc = iq_alloc_samples;
@@ -1264,11 +1463,21 @@ int sydr_trk_run(const void* d_iq, int iq_dtype, long long iq_alloc_samples, dou
     P.append = cfg ? (cfg->append != 0) : 0;
     P.iq_len = cfg ? cfg->iq_len : 0;
     P.seg = (g_trk_mode == 0) ? 1 : 0;
+    P.resume = 0;
     P.prof = g_trk_prof;
     cudaStream_t s = (cudaStream_t)stream;
-    SYDR_DISPATCH_VPC(launch_trk, iq_dtype, vpc, P, n_channels, cluster, threads, s)
-    set_error("sydr_trk_run: no kernel for this chunk size");
-    return SYDR_ERR_UNSUPPORTED;
+    if (lean) {
+        TrkParams PL = P;
+        PL.use_tma = 0;
+        const int lt = (!auto_shape && threads > 0) ? threads : kLeanThreads;
+        const int rc2 = dispatch_trk(iq_dtype, vpc, PL, n_channels, 1, lt, 1, s);
+        if (rc2 != SYDR_OK) return rc2;
+        // The general instantiation follows on the same stream: channels the LEAN kernel finished
+        // exit at once; a channel it stopped in front of an epoch it cannot serve continues here.
+        P.resume = 1;
+        if (auto_shape) threads = kTrkMaxThreads;
+    }
+    return dispatch_trk(iq_dtype, vpc, P, n_channels, cluster, threads, 0, s);
 }
 
 int sydr_trk_state_init(sydr_trk_state* h, int prn, double fs, double carrier_freq, long long start_sample,
