@@ -163,6 +163,54 @@ def run_reference(args, rank, world):
     print(json.dumps(line))
 
 
+def throughput_stress(dev, n_rec, seconds, tf_peak, steps=3):
+    """BASELINE.json configs[4] on this GPU: n_rec concurrent recordings x 12 channels of closed-loop
+    tracking in one launch (K-TRK throughput instantiation).  This is where the kernel's roofline
+    fraction is meaningful: a single 12-channel recording is bound by the serial epoch chain
+    (SURVEY.md section 8d)."""
+    import torch
+    from sydr_b200 import synth
+    from sydr_b200.engine import AcquisitionEngine, TrackingEngine, make_trk_states
+    n = int(round(seconds * FS))
+    pad = 2048
+    buf = torch.zeros(n_rec * (2 * n + pad) + 4096, dtype=torch.int16, device=dev)
+    acq = AcquisitionEngine(FS, 0.0, ACQ["doppler_range"], ACQ["doppler_step"], ACQ["coh"], ACQ["noncoh"], list(synth.PRNS_12),
+                            device=dev)
+    chans, truth = [], []
+    for r in range(n_rec):
+        sc = synth.make_scenario(FS, NBITS, seconds, synth.PRNS_12, 1005 + r, 250.0)
+        base = r * (2 * n + pad)
+        buf[base:base + 2 * n] = synth.generate_iq_torch(sc, device=dev)
+        for p in acq.run(buf[base:base + 2 * n])["peaks"]:
+            carrier, _, cur = acq.handoff(p)
+            chans.append(dict(prn=int(p["prn"]), carrier_freq=carrier, start_sample=cur, iq_base=base // 2, iq_len=n))
+        truth += [s.doppler for s in sc.sats]
+    acq.close()
+    st = make_trk_states(FS, chans)
+    eng = TrackingEngine(FS, st, int(seconds * 1000) + 8, device=dev)
+    ms = []
+    for _ in range(steps + 1):
+        eng.reset(st)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); eng.launch(buf); e1.record(); torch.cuda.synchronize()
+        ms.append(e0.elapsed_time(e1))
+    ms = float(np.mean(ms[1:]))
+    res = eng.fetch()
+    err = max(abs(r["carrier_freq"][-1] - t) for r, t in zip(res, truth))
+    if err > 25.0:
+        raise SystemExit(f"throughput stress: tracking lost (|df| = {err:.1f} Hz)")
+    samples_ch = float(sum(r["n"].sum() for r in res))
+    ach = FLOP_PER_SAMPLE_CH * samples_ch / (ms * 1e-3) / 1e12
+    del buf
+    return {"workload": f"{n_rec} recordings x 12 channels, 25 MS/s int16, {seconds:g} s, one launch on one GPU",
+            "kernel": "trk_borre_kernel (throughput instantiation)", "ms": ms, "channels": len(chans),
+            "us_per_epoch_all_channels": ms * 1e3 / np.mean([len(r) for r in res]), "rtf": seconds * 1e3 / ms,
+            "Msamples_per_s": n_rec * n * np.mean([len(r) for r in res]) / (seconds * 1e3) / (ms * 1e-3) / 1e6,
+            "Gsample_channels_per_s": samples_ch / (ms * 1e-3) / 1e9, "bound": "fp32", "achieved": ach, "peak": tf_peak,
+            "unit": "TFLOP/s", "frac": ach / tf_peak if tf_peak else None,
+            "hbm_GBps": (4.0 * n_rec * n + 128.0 * samples_ch / (FS * 1e-3)) / (ms * 1e-3) / 1e9}
+
+
 def workload_config(args, world):
     return {"workload": f"cfg3-format recording per GPU (25 MS/s int16 IQ, 12 PRNs @45 dB-Hz, {args.chunk_seconds:g} s chunk "
                         "per step): 32-PRN PCPS acquisition (+-5 kHz/250 Hz, 1 ms x 10) + 12-channel closed-loop E/P/L tracking",
@@ -182,6 +230,8 @@ def main():
     ap.add_argument("--threads", type=int, default=0)
     ap.add_argument("--no-tma", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--stress-recordings", type=int, default=32, help="recordings of the cfg-5 throughput measurement (0 = skip)")
+    ap.add_argument("--stress-seconds", type=float, default=0.5)
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -320,6 +370,8 @@ def main():
                     "kernels": {"trk_borre_kernel": {"ms": ms_trk, "tflops": trk_flop / (ms_trk * 1e-3) / 1e12,
                                                      "us_per_epoch": ms_trk * 1e3 / (chunk_samples / (FS * 1e-3))},
                                 "acq (fwd+ifft+reduce)": {"ms": ms_acq, "tflops": acq_flop / (ms_acq * 1e-3) / 1e12}}}
+        if args.stress_recordings > 0 and world == 1:
+            roofline["throughput_mode"] = throughput_stress(dev, args.stress_recordings, args.stress_seconds, tfv.value)
         line = {"metric": "cold acquisition (32 PRN) + 12-channel tracking throughput", "value": value, "unit": "Msamples/s",
                 "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev / args.steps,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",

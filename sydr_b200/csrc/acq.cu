@@ -316,8 +316,11 @@ __global__ void __launch_bounds__(P::T) acq_ifft_kernel(const AcqDev A, sydr_acq
     __shared__ float x_m2[2];
 
     const int h = (HALVES == 2) ? (int)cluster_ctarank() : 0;
-    const int rowid = blockIdx.x / HALVES;               // prn_slot * n_rows + row
-    const int slot = rowid / A.n_rows, row = rowid - slot * A.n_rows;
+    // CTAs are ordered row-major over (Doppler row, PRN): the ~148 resident CTAs read a handful of
+    // forward spectra Y[row] (all PRNs share them) and the 32 code spectra, which stay in L2
+    const int cta = blockIdx.x / HALVES;
+    const int row = cta / A.n_prn, slot = cta - row * A.n_prn;
+    const int rowid = slot * A.n_rows + row;              // index into rows[] / maps[]
     const float2* __restrict__ C = A.code_spec + (size_t)slot * NF;
     float2* cbuf = fbuf + NH;                             // code spectrum copy (CODE_IN_SMEM)
     if (CODE_IN_SMEM) {

@@ -174,6 +174,35 @@ def test_closed_loop_vs_reference_channel(golden, name, cfg):
         assert np.median(e) <= 1e-3
 
 
+def test_throughput_kernel_hands_over_to_general(golden):
+    """Quarter-chip spacing is off the half-chip lattice: the throughput instantiation stops in front
+    of the first epoch (status kNeedGeneral) and the general kernel queued behind it tracks the
+    channel; the result must equal a launch that used the general kernel from the start."""
+    from oracle import sydr_oracle as O
+    from sydr_b200.engine import TrackingEngine, make_trk_states, to_device_iq
+    g = golden("loop.npz")
+    meta, prns = g["fs25_meta"], g["fs25_prns"]
+    sc, iq = H.loop_input(meta, prns)
+    fs = float(meta[0])
+    chans = []
+    for prn in prns:
+        acq = g[f"fs25_acq_{int(prn)}"]
+        carrier, _, cur = O.acquisition_handoff(int(acq[1]), int(acq[2]), 0.0, 5000.0, float(meta[4]), 0, 250000, 25000)
+        chans.append(dict(prn=int(prn), carrier_freq=carrier, start_sample=cur, iq_len=len(iq) // 2))
+    cfg = dict(correlator_early=-0.25, correlator_late=0.25)
+    d_iq = to_device_iq(iq)
+    ref = TrackingEngine(fs, make_trk_states(fs, chans, cfg), max_epochs=300, cluster=1, threads=0, use_tma=True)
+    a = ref.run(d_iq)
+    lean = TrackingEngine(fs, make_trk_states(fs, chans, cfg), max_epochs=300, cluster=1, threads=256, use_tma=False)
+    b = lean.run(d_iq)
+    assert (lean.states()["status"] == 0).all()
+    for ra, rb in zip(a, b):
+        assert len(ra) == len(rb) and len(ra) > 100
+        assert np.array_equal(ra["start"], rb["start"]) and np.array_equal(ra["n"], rb["n"])
+        assert corr_err(rb["corr"], ra["corr"]).max() <= 1e-5
+        assert np.abs(ra["carrier_freq"] - rb["carrier_freq"]).max() <= 1e-3
+
+
 def test_bit_identical_across_launch_splits(golden):
     """Stopping after k epochs and resuming gives the same trajectory as one launch (state round trip)."""
     from oracle import sydr_oracle as O
