@@ -571,7 +571,7 @@ using Plan10000 = Plan<10000, 512, 10, 10, 10, 10, 1>;
 using Plan12500 = Plan<12500, 512, 10, 10, 5, 5, 5>;
 using Plan16000 = Plan<16000, 512, 10, 10, 10, 16, 1>;
 using Plan20000 = Plan<20000, 512, 10, 10, 10, 20, 1>;
-using Plan25000 = Plan<25000, 512, 10, 10, 10, 5, 5>;
+using Plan25000 = Plan<25000, 512, 10, 10, 10, 25, 1>;
 
 struct PlanShape { int nh, halves; };
 
