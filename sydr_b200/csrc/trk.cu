@@ -1096,7 +1096,7 @@ __global__ void __launch_bounds__(LEAN ? kLeanThreads : kTrkMaxThreads, LEAN ? 3
             if (sc.n_req <= 0 || (long long)sc.n_req + SPV > (long long)S * Q * C) status = SYDR_ERR_STATE;
             bool stop = (status != 0) || (sh.rec_base + epoch >= P.max_epochs) || (sc.cur + sc.n_req > sh.cfgs.iq_len);
             double t_start = 0.0, t_step = 0.0, t_stop = 0.0;
-            int fast = 0, seg = 0;
+            int fast = 0, seg = 0, hb = 0, rounds = 0;
             if (!stop) {
                 // tap constants (numpy linspace arithmetic, tracking.py:110-112), lane s < 3 = correlator s
                 const double dn = i2d(sc.n_req);
@@ -1104,7 +1104,7 @@ __global__ void __launch_bounds__(LEAN ? kLeanThreads : kTrkMaxThreads, LEAN ? 3
                 t_start = dadd(sc.rem_code, sh.cfgs.spacing[min(lane, 2)]);
                 t_stop = dadd(dmul(sc.code_step, dn), t_start);
                 t_step = ddiv_by(dsub(t_stop, t_start), dn, sc.inv_n);
-                fast = __all_sync(full, sc.inv_step >= (double)(C + 1));             // a chip outlasts a chunk
+                fast = __all_sync(full, sc.inv_step >= (double)(C + 1)) && !(NV > 0 && sh.seg_ok);   // a chip outlasts a chunk
                 if (NV > 0) {                                                        // every code index inside the padded code
                     const bool in = (t_start > -0.999) && (t_stop < (double)(kPaddedChips - 1) - 0.001);
                     seg = sh.seg_ok && __all_sync(full, in) && seg_epoch_ok<(NV > 0 ? NV : 1)>(0.0, 0.0, sc.inv_step);
@@ -1113,6 +1113,18 @@ __global__ void __launch_bounds__(LEAN ? kLeanThreads : kTrkMaxThreads, LEAN ? 3
                     stop = true;
                     status = kNeedGeneral;
                 }
+                if (NV > 0) {
+                    // lattice index in front of this CTA's first sample, from the prompt tap; every lane
+                    // evaluates it next to its own tap so that no single-lane FP64 tail extends the chain
+                    const double p_start = dadd(sc.rem_code, sh.cfgs.spacing[1]);
+                    const double p_stop = dadd(dmul(sc.code_step, dn), p_start);
+                    const double p_step = ddiv_by(dsub(p_stop, p_start), dn, sc.inv_n);
+                    const int lead_s = (int)(sc.cur & (long long)(SPV - 1));
+                    const int wlo = max((int)rank * Q * C - lead_s, 0);
+                    hb = ceil_to_int(2.0 * code_phase(wlo, p_start, p_step)) - 1;
+                    // segments hb .. ceil(2 phase(n)) cover the epoch; W (a power of two) warps take 32 per round
+                    if (LEAN) rounds = (ceil_to_int(2.0 * p_stop) - hb + 32 * W) >> (5 + 31 - __clz(W));
+                }
             }
             if (!stop) {
                 SYDR_TICK(8)
@@ -1120,14 +1132,10 @@ __global__ void __launch_bounds__(LEAN ? kLeanThreads : kTrkMaxThreads, LEAN ? 3
                     sh.ctl.ec.start[lane] = t_start;
                     sh.ctl.ec.step[lane] = t_step;
                     sh.ctl.ec.inv_step[lane] = sc.inv_step;                        // ~1/step': estimates only
-                    if (NV > 0 && lane == 1) {                                       // prompt tap: lattice index of this CTA's first sample
-                        const int lead_s = (int)(sc.cur & (long long)(SPV - 1));
-                        const int wlo = max((int)rank * Q * C - lead_s, 0);
-                        const int hb = ceil_to_int(2.0 * code_phase(wlo, t_start, t_step)) - 1;
+                    if (NV > 0 && lane == 1) {
                         sh.ctl.ec.seg = seg;
                         sh.ctl.ec.hb = hb;
-                        // segments hb .. ceil(2 phase(n)) cover the epoch; W warps take 32 per round
-                        sh.ctl.ec.rounds = (ceil_to_int(2.0 * t_stop) - hb + 32 * W) / (32 * W);
+                        sh.ctl.ec.rounds = rounds;
                     }
                 } else if (lane == 3) {
                     sh.ctl.ec.n = sc.n_req;
@@ -1154,7 +1162,9 @@ __global__ void __launch_bounds__(LEAN ? kLeanThreads : kTrkMaxThreads, LEAN ? 3
                 constexpr int RB = RoundTraits<(NV > 0 ? NV : 1)>::kRotBase;
                 carrier_table_entry(ca, RB + lane, sh.rot[lane].x, sh.rot[lane].y);
                 if (lane < kRotMax - 32) carrier_table_entry(ca, RB + 32 + lane, sh.rot[32 + lane].x, sh.rot[32 + lane].y);
-            } else if (lane < kMaxChunk) {
+            } else if (lane < kMaxChunk && !(NV > 0 && sh.seg_ok)) {
+                // only the split-sum chunk path reads the table; a channel on the half-chip lattice
+                // never takes it (an epoch the segment path cannot serve uses the per-sample masks)
                 carrier_table_entry(ca, lane, sh.ctl.ec.wtab[lane][0], sh.ctl.ec.wtab[lane][1]);
             }
             SYDR_TICK1(13)                             // carrier warp: constants of the next epoch
@@ -1447,7 +1457,8 @@ int sydr_trk_run(const void* d_iq, int iq_dtype, long long iq_alloc_samples, dou
     const bool seg_fits = nv > 0 && g_trk_mode == 0 && half_chip >= 2 * nv - 2 + 0.05 && half_chip <= 2 * nv - 1 - 0.05;
     const bool auto_shape = !cfg || cfg->cluster <= 0;
     const bool lean = seg_fits && ((auto_shape && cluster == 1) ||
-                                   (!auto_shape && cluster == 1 && !use_tma && threads > 0 && threads <= kLeanThreads));
+                                   (!auto_shape && cluster == 1 && !use_tma && threads > 0 && threads <= kLeanThreads &&
+                                    (threads & (threads - 1)) == 0));   // power of two: rounds by shift
 
     TrkParams P;
     P.iq = reinterpret_cast<const uint8_t*>(d_iq);

@@ -180,19 +180,17 @@ def make_trk_states(fs, channels, cfg=None) -> np.ndarray:
     channels = list(channels)
     st = np.zeros(len(channels), dtype=L.TRK_STATE_DTYPE)
     code_step = CODE_FREQ / fs
-    for i, ch in enumerate(channels):
-        s = st[i]
-        s["prn"] = ch["prn"]
-        s["iq_base"] = ch.get("iq_base", 0)
-        s["iq_len"] = ch.get("iq_len", 0)
-        s["cur"] = ch["start_sample"]
-        s["carrier_freq"] = ch["carrier_freq"]
-        s["code_freq"] = CODE_FREQ
-        s["code_step"] = code_step
-        s["n_req"] = int(np.ceil((CODE_CHIPS - 0.0) / code_step))
-        s["dll_tau1"], s["dll_tau2"], s["dll_pdi"] = dll_t1, dll_t2, c["dll_pdi"]
-        s["pll_tau1"], s["pll_tau2"], s["pll_pdi"] = pll_t1, pll_t2, c["pll_pdi"]
-        s["spacing"] = (c["correlator_early"], c["correlator_prompt"], c["correlator_late"])
+    st["prn"] = [ch["prn"] for ch in channels]
+    st["iq_base"] = [ch.get("iq_base", 0) for ch in channels]
+    st["iq_len"] = [ch.get("iq_len", 0) for ch in channels]
+    st["cur"] = [ch["start_sample"] for ch in channels]
+    st["carrier_freq"] = [ch["carrier_freq"] for ch in channels]
+    st["code_freq"] = CODE_FREQ
+    st["code_step"] = code_step
+    st["n_req"] = int(np.ceil((CODE_CHIPS - 0.0) / code_step))
+    st["dll_tau1"], st["dll_tau2"], st["dll_pdi"] = dll_t1, dll_t2, c["dll_pdi"]
+    st["pll_tau1"], st["pll_tau2"], st["pll_pdi"] = pll_t1, pll_t2, c["pll_pdi"]
+    st["spacing"] = (c["correlator_early"], c["correlator_prompt"], c["correlator_late"])
     return st
 
 
@@ -226,6 +224,9 @@ class TrackingEngine:
         self._states = torch.from_numpy(st.view(np.uint8).reshape(-1).copy()).to(self.device)
         self._out = torch.empty(self.n_ch * self.max_epochs * 128, dtype=torch.uint8, device=self.device)
         self._nep = torch.zeros(self.n_ch, dtype=torch.int32, device=self.device)
+        # pinned staging for the results: one asynchronous D2H per fetch, no pageable bounce
+        self._out_host = torch.empty(self.n_ch * self.max_epochs * 128, dtype=torch.uint8, pin_memory=True)
+        self._nep_host = torch.zeros(self.n_ch, dtype=torch.int32, pin_memory=True)
 
     def set_iq_len(self, iq_len):
         """Update the number of valid samples per channel (streaming: more data arrived)."""
@@ -257,8 +258,11 @@ class TrackingEngine:
         return self._states.cpu().numpy().view(L.TRK_STATE_DTYPE).copy()
 
     def fetch(self):
-        nep = self._nep.cpu().numpy()
-        out = self._out.cpu().numpy().view(L.TRK_EPOCH_DTYPE).reshape(self.n_ch, self.max_epochs)
+        self._nep_host.copy_(self._nep, non_blocking=True)
+        self._out_host.copy_(self._out, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        nep = self._nep_host.numpy()
+        out = self._out_host.numpy().view(L.TRK_EPOCH_DTYPE).reshape(self.n_ch, self.max_epochs)
         return [out[c, :nep[c]].copy() for c in range(self.n_ch)]
 
     def run(self, iq_dev: torch.Tensor, stream=None):
