@@ -31,6 +31,11 @@ SEARCH_PRNS = list(range(1, 33))
 N_CHANNELS = 12
 ACQ = dict(doppler_range=5000.0, doppler_step=250.0, coh=1, noncoh=10)
 FLOP_PER_SAMPLE_CH = 31.0
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the
+# `ncu --set full` capture of this very workload (tools/ncu_bench.py, 2 s chunk, 12 channels;
+# profiles/r1_ncu_summary.txt).  Algorithmic bytes of the same launch: 200.0 MB IQ + 3.07 MB records.
+NCU_TRAFFIC_BYTES = {"trk_borre_kernel": (199.267584e6 + 6.576384e6, 2.0),
+                     "acq_ifft_kernel": (88.491264e6 + 4.472320e6, None)}
 
 
 def f_acq(n):                                  # flop per (PRN, bin, code period), SURVEY.md §8(d)
@@ -360,8 +365,12 @@ def main():
         acq_flop = len(SEARCH_PRNS) * 41 * ACQ["coh"] * ACQ["noncoh"] * f_acq(n_code)
         dominant = "trk_borre_kernel" if ms_trk >= ms_acq else "acq_ifft_kernel"
         ach = (trk_flop / (ms_trk * 1e-3) / 1e12) if dominant == "trk_borre_kernel" else (acq_flop / (ms_acq * 1e-3) / 1e12)
+        tr_bytes, tr_chunk = NCU_TRAFFIC_BYTES[dominant]
+        traffic = tr_bytes * (args.chunk_seconds / tr_chunk if tr_chunk else 1.0)
         roofline = {"kernel": dominant, "bound": "fp32", "achieved": ach, "peak": tfv.value, "unit": "TFLOP/s",
-                    "frac": ach / tfv.value if tfv.value else None, "traffic": None,
+                    "frac": ach / tfv.value if tfv.value else None, "traffic": traffic,
+                    "traffic_note": "DRAM bytes per launch (ncu --set full, profiles/r1_ncu_summary.txt); algorithmic bytes per "
+                                    f"launch {trk_bytes:.4g}" if dominant == "trk_borre_kernel" else "DRAM bytes per launch (ncu)",
                     "peak_source": f"FP32 FMA chain measured in this run ({clkv.value:.0f} MHz max clock)",
                     "note": "12 channels occupy <= 96 of 148 SMs and every channel is a serial chain of 1 ms epochs: "
                             "the bound is per-epoch latency, not the FP32 or HBM roof (DESIGN.md §4)",
