@@ -201,7 +201,7 @@ def throughput_stress(dev, n_rec, seconds, tf_peak, steps=3):
         ms.append(e0.elapsed_time(e1))
     ms = float(np.mean(ms[1:]))
     res = eng.fetch()
-    err = max(abs(r["carrier_freq"][-1] - t) for r, t in zip(res, truth))
+    err = max(abs(float(np.mean(r["carrier_freq"][-100:])) - t) for r, t in zip(res, truth))
     if err > 25.0:
         raise SystemExit(f"throughput stress: tracking lost (|df| = {err:.1f} Hz)")
     samples_ch = float(sum(r["n"].sum() for r in res))
@@ -286,7 +286,8 @@ def main():
     out = step_e2e()
     torch.cuda.synchronize()
     truth = {s.prn: s.doppler for s in sc.sats}
-    got = {c["prn"]: e["carrier_freq"][-1] for c, e in zip(out["channels"], out["epochs"])}
+    # the loop output jitters by a few Hz epoch to epoch at 45 dB-Hz: gate on the mean of the last 200 epochs
+    got = {c["prn"]: float(np.mean(e["carrier_freq"][-200:])) for c, e in zip(out["channels"], out["epochs"])}
     bad = [p for p in truth if p not in got or abs(got[p] - truth[p]) > 5.0]
     if bad or min(len(e) for e in out["epochs"]) < int(args.chunk_seconds * 1000) - 12:
         raise SystemExit(f"rank {rank}: tracking did not converge to the synthetic truth for PRNs {bad}")
