@@ -44,24 +44,65 @@ def f_acq(n):                                  # flop per (PRN, bin, code period
 
 # ----------------------------------------------------------------------------------------
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md): one
-    long-lived `nvidia-smi -lms` process, so that sampling does not disturb the timed loop."""
+    """SM clock and throttle reasons during the timed region (B200_PROFILING.md): NVML polled every
+    few milliseconds from a thread (the timed region lasts ~0.1 s, too short for `nvidia-smi -lms`);
+    falls back to one long-lived `nvidia-smi -lms` process when NVML is unavailable."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.index, self.proc = index, None
+        self.index, self.proc, self.thread, self.rows, self.stop_flag = index, None, None, [], False
+        self.max_mhz = None
+
+    def _poll(self):
+        import pynvml as N
+        h = self.handle
+        while not self.stop_flag:
+            try:
+                mhz = N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM)
+                try:
+                    why = N.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except Exception:
+                    why = N.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                self.rows.append((mhz, why))
+            except Exception:
+                pass
+            time.sleep(0.004)
 
     def start(self):
         try:
+            import threading
+            import pynvml as N
+            N.nvmlInit()
+            self.N = N
+            self.handle = N.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = float(N.nvmlDeviceGetMaxClockInfo(self.handle, N.NVML_CLOCK_SM))
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.thread = None
+        try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "250"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except Exception:
             self.proc = None
 
     def stop(self):
+        if self.thread is not None:
+            self.stop_flag = True
+            self.thread.join(timeout=2)
+            N = self.N
+            bits = {"hw_slowdown": getattr(N, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                    "hw_thermal_slowdown": getattr(N, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                    "sw_thermal_slowdown": getattr(N, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                    "sw_power_cap": getattr(N, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
+            sm = [float(m) for m, _ in self.rows]
+            reasons = sorted({n for _, w in self.rows for n, b in bits.items() if w & b})
+            return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": self.max_mhz, "reasons": reasons,
+                    "samples": len(sm), "source": "nvml"}
         rows = []
         if self.proc is not None:
             self.proc.terminate()
@@ -75,7 +116,7 @@ class ClockSampler:
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = sorted({n for r in rows if len(r) >= 8 for n, v in zip(names, r[4:8]) if v.lower().startswith("active")})
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+                "reasons": reasons, "samples": len(sm), "source": "nvidia-smi"}
 
 
 # ----------------------------------------------------------------------------------------

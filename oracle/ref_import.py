@@ -94,3 +94,14 @@ def load_channel():
     ns.ChannelMessage = ChannelMessage
     ns.ChannelState = ChannelState
     return ns
+
+
+def load_channel_kaplan():
+    """The Kaplan channel variant (sydr/channel/channel_l1ca_kaplan.py) for in-process driving."""
+    ns = load_channel()
+    from sydr.channel.channel_l1ca_kaplan import ChannelL1CA_Kaplan
+    from sydr.utils.enumerations import LoopLockState, TrackingFlags
+    ns.ChannelL1CA_Kaplan = ChannelL1CA_Kaplan
+    ns.LoopLockState = LoopLockState
+    ns.TrackingFlags = TrackingFlags
+    return ns

@@ -96,3 +96,25 @@ def BorreLoopFilter(input: float, memory: float, tau1: float, tau2: float, pdi: 
     output = tau2 / tau1 * (input - memory)
     output += pdi / tau1 * input
     return output
+
+
+def FLLassistedPLL_2ndOrder(phaseInput: float, freqInput: float, w0f: float, w0p: float, a2: float,
+                            integrationTime: float, velMemory: float):
+    """2nd-order PLL assisted by a 1st-order FLL [Kaplan, 2006, p180-182], sydr/dsp/tracking.py:246-279.
+    Returns (output, velMemory)."""
+    update = (phaseInput * w0p ** 2 + freqInput * w0f) * integrationTime
+    output = update + velMemory
+    output += phaseInput * a2 * w0p
+    return output, update
+
+
+def FLLassistedPLL_3rdOrder(phaseInput: float, freqInput: float, w0f: float, w0p: float, a2: float, a3: float,
+                            b3: float, integrationTime: float, velMemory: float, accMemory: float):
+    """3rd-order PLL assisted by a 2nd-order FLL, sydr/dsp/tracking.py:283-325.
+    Returns (output, velMemory, accMemory)."""
+    acc_update = (phaseInput * w0p ** 3 + freqInput * w0f ** 2) * integrationTime
+    output = acc_update + accMemory
+    vel_update = (output + (phaseInput * a3 * w0p ** 2 + freqInput * a2 * w0f)) * integrationTime
+    output = vel_update + velMemory
+    output += phaseInput * b3 * w0p
+    return output, vel_update, acc_update

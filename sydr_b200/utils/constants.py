@@ -13,3 +13,11 @@ LNAV_WORD_SIZE = 30
 GPS_L1CA_CODE_SIZE_BITS = 1023
 GPS_L1CA_CODE_FREQ = 1.023e6
 GPS_L1CA_CODE_MS = 1
+
+# Digital loop filter constants [Kaplan, 2006, p180] (constants.py:80-85)
+W0_BANDWIDTH_1 = 0.25
+W0_BANDWIDTH_2 = 0.53
+W0_BANDWIDTH_3 = 0.7845
+W0_SCALE_A2 = 1.414
+W0_SCALE_A3 = 1.1
+W0_SCALE_B3 = 2.4

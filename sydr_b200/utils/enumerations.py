@@ -69,3 +69,15 @@ class TrackingFlags(IntEnum):
 
     def __str__(self):
         return str(self.name)
+
+
+@unique
+class LoopLockState(IntEnum):
+    """Carrier loop state of the Kaplan channel, sydr/utils/enumerations.py:143-150."""
+    UNKNOWN = 0
+    PULL_IN = 1
+    WIDE_TRACK = 2
+    NARROW_TRACK = 3
+
+    def __str__(self):
+        return str(self.name)

@@ -302,6 +302,57 @@ def g_channel(R):
     save("channel.npz", **out)
 
 
+KAPLAN_TRK_CFG = {  # config/channels/channel_GPS_L1CA_kaplan.ini [TRACKING]
+    "correlator_epl_wide": "0.5", "correlator_epl_narrow": "0.5", "dll_threshold": "10.0", "dll_damping_ratio": "0.7",
+    "dll_noise_bandwidth": "2.0", "dll_loop_gain": "1.0", "dll_pdi": "0.001", "pll_bandwidth_wide": "25.0",
+    "pll_bandwidth_narrow": "15.0", "pll_threshold_wide": "0.5", "pll_threshold_narrow": "0.8",
+    "fll_bandwidth_pullin": "100.0", "fll_bandwidth_wide": "50.0", "fll_bandwidth_narrow": "15.0",
+    "fll_threshold_wide": "0.5", "fll_threshold_narrow": "0.8"}
+KAPLAN_CASE = (4e6, 8, 31, 2600, (3, 19), 250)      # fs, bits, seed, ms, PRNs, Doppler step
+
+
+def g_kaplan(R):
+    """The live reference ChannelL1CA_Kaplan driven in-process: every tracking packet plus the NCO
+    members after it, and the per-tick flags / state."""
+    C = ref_import.load_channel_kaplan()
+    fs, nbits, seed, ms, prns, ds = KAPLAN_CASE
+    sc = synth.make_scenario(fs, nbits, ms * 1e-3, prns, seed, float(ds))
+    iq = synth.generate_iq(sc)
+    x = synth.to_complex(iq)
+    acq_cfg = {"doppler_range": "5000", "doppler_steps": str(ds), "coherent_integration": "1",
+               "non_coherent_integration": "10", "threshold": "1.5"}
+    out = {}
+    for prn in prns:
+        cfg = {"filepath": "none", "sampling_frequency": str(fs), "is_complex": "true",
+               "intermediate_frequency": "0.0", "data_size": "8"}
+        rf = C.RFSignal(cfg)
+        spm = rf.samplesPerMs
+        buf = C.CircularBuffer(int(fs * 1e-3 * 100), np.complex128)
+        ch = C.ChannelL1CA_Kaplan(0, buf, None, rf, {"ACQUISITION": acq_cfg, "TRACKING": KAPLAN_TRK_CFG})
+        ch.setSatellite(prn)
+        rows, acq = [], None
+        for tick in range(ms):
+            buf.shift(x[tick * spm:(tick + 1) * spm])
+            for r in ch._processHandler():
+                if r["type"] == C.ChannelMessage.ACQUISITION_UPDATE:
+                    acq = (tick, r["frequency_idx"], r["code_idx"], r["peak_ratio"], r["carrierFrequency"], ch.currentSample)
+                elif r["type"] == C.ChannelMessage.TRACKING_UPDATE:
+                    rows.append([tick, r["i_early"], r["q_early"], r["i_prompt"], r["q_prompt"], r["i_late"], r["q_late"],
+                                 r["dll"], r["pll"], r["fll"], r["carrier_frequency"], r["code_frequency"],
+                                 r["carrier_frequency_error"], r["code_frequency_error"], r["cn0"], r["pll_lock"],
+                                 r["fll_lock"], int(r["lock_state"]), int(ch.trackFlags), ch.remainingCode,
+                                 ch.remainingCarrier, ch.track_requiredSamples, ch.currentSample, ch.navBitsCounter])
+        out[f"acq_{prn}"] = np.array(acq, dtype=np.float64)
+        out[f"trk_{prn}"] = np.array(rows, dtype=np.float64)
+        st = out[f"trk_{prn}"][:, 17]
+        print(f"  kaplan PRN {prn}: {len(rows)} epochs, lock states {sorted(set(st.astype(int)))}, "
+              f"first WIDE {np.argmax(st == 2)}, first NARROW {np.argmax(st == 3)}, flags {int(ch.trackFlags)}")
+    out["meta"] = np.array([fs, nbits, seed, ms, ds], dtype=np.float64)
+    out["prns"] = np.array(prns)
+    out["sha"] = sha(iq)
+    save("kaplan.npz", **out)
+
+
 def g_decoding(R):
     """Inputs and the reference's outputs for LNAV_CheckPreambule / LNAV_DecodeTOW / Prompt2Bit."""
     from sydr.dsp import decoding as RD
@@ -360,6 +411,7 @@ def main():
     a = ap.parse_args()
     R = ref_import.load()
     groups = {"codes": g_codes, "peaks": g_peaks, "acq": g_acq, "epl": g_epl, "loop": g_loop, "channel": g_channel,
+              "kaplan": g_kaplan,
               "decoding": g_decoding}
     for name, fn in groups.items():
         if a.only and name not in a.only and not (name == "acq" and any(o in ACQ_CASES for o in a.only)):
