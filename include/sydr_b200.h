@@ -219,6 +219,33 @@ int sydr_trk_state_init(sydr_trk_state* h_state, int prn, double fs, double carr
 int sydr_convert_to_f32(const void* d_in, int iq_dtype, long long n_samples, float* d_out_c64,
                         void* stream);
 
+/* ------------------------------------------------------------------ nav bits --------- */
+/* Bit synchronisation + navigation-bit accumulation on the device (K-NAV): the scalar state
+ * machine ChannelL1CA runs on every tracking result (channel_l1ca_borre.py:398-413 bit-sync
+ * test, L367-373 / L577-591 / L626-627 prompt history, L455-491 20 prompts -> Prompt2Bit,
+ * sydr/dsp/decoding.py:16-27).  The members are the channel attributes of the same meaning. */
+typedef struct {
+    int64_t code_counter;   /* codeCounter: tracking epochs ingested so far                  */
+    int64_t sync_epoch;     /* epoch index at which BIT_SYNC was raised; -1 = not yet         */
+    double  prev_iprompt;   /* iPrompt of the previous epoch                                  */
+    double  row19;          /* correlatorsBuffer[19, IDX_I_PROMPT] (read once, at sync)       */
+    double  nav_sum;        /* navPromptSum                                                   */
+    int32_t nav_count;      /* navPromptSumCounter                                            */
+    int32_t n_bits;         /* bits emitted so far (all calls)                                */
+} sydr_nav_state;           /* 48 bytes */
+
+int sydr_nav_state_init(sydr_nav_state* h_state);
+
+/* Consume the tracking records d_epochs[ch][first_epoch .. d_nepochs[ch]) of n_channels
+ * channels (the arrays sydr_trk_run fills) and emit the navigation bits they complete:
+ * d_bits[ch][0 .. d_nbits[ch]) (0/1, Prompt2Bit with bit0 = 0) and, if d_bit_sums is not
+ * NULL, the 20-epoch prompt sums they are the signs of (bit-identical to navPromptSum).  At
+ * most max_bits bits per channel are stored per call.  d_nav carries the state across calls,
+ * so a recording can be consumed in pieces of any length. */
+int sydr_nav_bits(const sydr_trk_epoch* d_epochs, int max_epochs, const int* d_nepochs, int first_epoch,
+                  sydr_nav_state* d_nav, int n_channels, signed char* d_bits, double* d_bit_sums,
+                  int max_bits, int* d_nbits, void* stream);
+
 /* ------------------------------------------------------------------ legacy C ABI ----- */
 /* The per-call entry points the reference's ctypes callers bind
  * (sydr/old/tracking/tracking_epl_c.py:31-96, sydr/old/acquisition/acquisition_pcps_c.py:32-66),

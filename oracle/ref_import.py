@@ -87,7 +87,8 @@ def load_channel():
     from sydr.channel.channel_l1ca_borre import ChannelL1CA
     from sydr.utils.circularbuffer import CircularBuffer
     from sydr.signal.rfsignal import RFSignal
-    from sydr.utils.enumerations import ChannelMessage, ChannelState
+    from sydr.utils.enumerations import ChannelMessage, ChannelState, TrackingFlags
+    ns.TrackingFlags = TrackingFlags
     ns.ChannelL1CA = ChannelL1CA
     ns.CircularBuffer = CircularBuffer
     ns.RFSignal = RFSignal

@@ -330,3 +330,68 @@ class BorreTrackOracle:
                 break
             out.append(self.step(rf_all))
         return out
+
+
+# ------------------------------------------------------------------------------------------
+# Bit synchronisation + navigation-bit accumulation (the scalar step right after the
+# correlators).  Plain Python loop, one iteration per tracking epoch.
+# ------------------------------------------------------------------------------------------
+LNAV_MS_PER_BIT = 20            # sydr/utils/constants.py
+MIN_CONVERGENCE_TIME = 100      # sydr/channel/channel_l1ca_borre.py:30
+
+
+class NavBitOracle:
+    """What ChannelL1CA does with the prompt of every tracking epoch
+    (sydr/channel/channel_l1ca_borre.py:367-373 prompt history, L398-413 bit-sync test, L414-419
+    flags and counters, L455-491 runDecoding up to Prompt2Bit, L577-591 resetPrompt, L626-627
+    history wrap; sydr/dsp/decoding.py:16-27 Prompt2Bit)."""
+
+    def __init__(self):
+        self.code_lock = False
+        self.bit_sync = False
+        self.code_counter = 0
+        self.i_prompt = 0.0
+        self.nb_prompt = 0
+        self.history = np.zeros(LNAV_MS_PER_BIT)            # correlatorsBuffer[:, IDX_I_PROMPT]
+        self.nav_sum = 0.0
+        self.nav_count = 0
+        self.bits = []
+        self.sums = []
+        self.sync_epoch = -1
+
+    def step(self, ip: float):
+        # runTracking
+        self.history[self.nb_prompt] = ip                                       # L367
+        self.nb_prompt += 1                                                     # L372
+        if not self.bit_sync:                                                   # L400
+            if self.code_lock and self.code_counter > MIN_CONVERGENCE_TIME \
+                    and np.sign(self.i_prompt) != np.sign(ip):                  # L402-404
+                self.bit_sync = True
+                self.sync_epoch = self.code_counter
+                self.nb_prompt = 0                                              # resetPrompt, L591
+        self.code_lock = True                                                   # L416
+        self.i_prompt = ip                                                      # L417
+        self.code_counter += 1                                                  # L419
+        # runDecoding
+        if not self.bit_sync:                                                   # L472-476
+            self.nav_sum = 0.0
+            self.nav_count = 0
+        else:
+            self.nav_sum += self.history[self.nb_prompt - 1]                    # L479 (index -1 on the sync epoch)
+            self.nav_count += 1
+            if self.nav_count == LNAV_MS_PER_BIT:                               # L483
+                self.bits.append(1 if self.nav_sum > 0 else 0)                  # Prompt2Bit
+                self.sums.append(self.nav_sum)
+                self.nav_sum = 0.0
+                self.nav_count = 0
+        # _processHandler tail
+        if self.nb_prompt == LNAV_MS_PER_BIT:                                   # L626-627
+            self.nb_prompt = 0
+
+
+def nav_bits(i_prompts):
+    """Bits, their 20-epoch sums and the synchronisation epoch for a prompt sequence."""
+    o = NavBitOracle()
+    for v in i_prompts:
+        o.step(float(v))
+    return np.array(o.bits, dtype=np.int8), np.array(o.sums, dtype=np.float64), o.sync_epoch, o

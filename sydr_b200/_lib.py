@@ -78,6 +78,9 @@ TRK_STATE_DTYPE = np.dtype([("iq_base", "<i8"), ("iq_len", "<i8"), ("cur", "<i8"
 TRK_EPOCH_DTYPE = np.dtype([("corr", "<f8", (6,)), ("dll", "<f8"), ("pll", "<f8"), ("carrier_freq", "<f8"),
                             ("code_freq", "<f8"), ("code_err", "<f8"), ("carrier_err", "<f8"),
                             ("start", "<f8"), ("n", "<f8"), ("rem_code", "<f8"), ("rem_carrier", "<f8")])
+NAV_STATE_DTYPE = np.dtype([("code_counter", "<i8"), ("sync_epoch", "<i8"), ("prev_iprompt", "<f8"),
+                            ("row19", "<f8"), ("nav_sum", "<f8"), ("nav_count", "<i4"), ("n_bits", "<i4")])
+assert NAV_STATE_DTYPE.itemsize == 48
 assert ACQ_PEAK_DTYPE.itemsize == C.sizeof(AcqPeak) == 24
 assert ACQ_ROW_DTYPE.itemsize == C.sizeof(AcqRow) == 16
 assert EPL_ARGS_DTYPE.itemsize == C.sizeof(EplArgs) == 72
@@ -112,6 +115,8 @@ SIGNATURES = {
     "sydr_trk_set_mode": (_i, [_i]),
     "sydr_trk_state_init": (_i, [_vp, _i, _d, _d, _ll] + [_d] * 11),
     "sydr_convert_to_f32": (_i, [_vp, _i, _ll, _vp, _vp]),
+    "sydr_nav_state_init": (_i, [_vp]),
+    "sydr_nav_bits": (_i, [_vp, _i, _vp, _i, _vp, _i, _vp, _vp, _i, _vp, _vp]),
     # legacy per-call ABI (sydr/c_functions/*.c)
     "generateReplica": (None, [_vp, _sz, _d, _d, _vp, _vp]),
     "getCorrelator": (None, [_vp, _vp, _vp, _sz, _d, _d, _d, _vp, _vp]),

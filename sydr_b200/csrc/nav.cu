@@ -1,0 +1,149 @@
+// K-NAV: bit synchronisation and navigation-bit accumulation on the device.
+//
+// Reference semantics (file:line in /root/reference):
+//   bit-sync test                     sydr/channel/channel_l1ca_borre.py:398-413
+//   prompt history / resetPrompt      sydr/channel/channel_l1ca_borre.py:367-373, 577-591, 626-627
+//   20-epoch prompt sum -> bit        sydr/channel/channel_l1ca_borre.py:455-491
+//   Prompt2Bit                        sydr/dsp/decoding.py:16-27
+//
+// The closed-loop tracking kernel leaves one 128-byte record per channel-epoch in HBM.  The
+// step the reference performs next on every one of them (per channel process, per ms) is a
+// scalar state machine: wait MIN_CONVERGENCE_TIME epochs, declare bit synchronisation at the
+// first sign change of the prompt in-phase sum, then add 20 prompts per bit and take the sign.
+// Doing it here means 50 bit/s per channel cross PCIe instead of 128 kB/s.
+//
+// One warp owns one channel.  Before synchronisation the lanes test 32 epochs per round and a
+// ballot picks the first sign change; after it every lane owns one bit and adds its 20 prompts
+// in the reference's order (sequential FP64 adds starting from 0.0), so the sums - not only
+// their signs - equal the reference's navPromptSum bit for bit.
+//
+// Quirk kept on purpose: on the synchronisation epoch resetPrompt() zeroes nbPrompt *before*
+// runDecoding reads correlatorsBuffer[nbPrompt - 1], so the first addend of the first bit is
+// row 19 of the 20-row prompt history (the prompt of the latest epoch whose index is 19 modulo
+// 20), not the synchronisation epoch's own prompt.
+#include <string.h>
+
+#include "common.cuh"
+
+namespace sydr {
+
+constexpr int kMsPerBit = 20;                 // LNAV_MS_PER_BIT, sydr/utils/constants.py
+constexpr long long kMinConvergence = 100;    // ChannelL1CA.MIN_CONVERGENCE_TIME (L30)
+constexpr int kIPromptSlot = 2;               // corr[2] of sydr_trk_epoch
+
+__device__ __forceinline__ int np_sign(double x) { return (x > 0.0) - (x < 0.0); }   // np.sign of a finite value
+
+__global__ void __launch_bounds__(32) nav_bits_kernel(const sydr_trk_epoch* __restrict__ epochs, int max_epochs,
+                                                      const int* __restrict__ nepochs, int first,
+                                                      sydr_nav_state* __restrict__ nav, int8_t* __restrict__ bits,
+                                                      double* __restrict__ bit_sums, int max_bits,
+                                                      int* __restrict__ nbits_out) {
+    const int ch = blockIdx.x, lane = threadIdx.x;
+    const unsigned full = 0xffffffffu;
+    const double* row = reinterpret_cast<const double*>(epochs + (long long)ch * max_epochs + first) + kIPromptSlot;
+    auto ip = [&](int k) { return row[(long long)k * (sizeof(sydr_trk_epoch) / sizeof(double))]; };
+    const int n = max(nepochs[ch] - first, 0);
+    sydr_nav_state s = nav[ch];
+    int k = 0;                                 // next local epoch to consume
+    int produced = 0;
+
+    if (s.sync_epoch < 0) {
+        // ---- L401-407: CODE_LOCK (set by the first epoch) and codeCounter > 100 and a sign change
+        int ks = -1;
+        for (int base = 0; base < n && ks < 0; base += 32) {
+            const int kk = base + lane;
+            bool hit = false;
+            if (kk < n) {
+                const long long cc = s.code_counter + kk;                 // codeCounter when epoch kk is ingested
+                const double prev = (kk == 0) ? s.prev_iprompt : ip(kk - 1);
+                hit = (cc >= 1) && (cc > kMinConvergence) && (np_sign(prev) != np_sign(ip(kk)));
+            }
+            const unsigned m = __ballot_sync(full, hit);
+            if (m) ks = base + __ffs(m) - 1;
+        }
+        const int upto = (ks >= 0) ? ks : n - 1;                          // last epoch written to the prompt history
+        if (upto >= 0) {
+            // row 19 of correlatorsBuffer: the latest epoch <= upto with (code_counter + k) % 20 == 19
+            const long long g = s.code_counter + upto;
+            const long long k19 = upto - ((g + 1) % kMsPerBit);
+            if (k19 >= 0) s.row19 = ip((int)k19);
+        }
+        if (ks < 0) {
+            if (n > 0) s.prev_iprompt = ip(n - 1);
+            s.code_counter += n;
+            if (lane == 0) { nav[ch] = s; nbits_out[ch] = 0; }
+            return;
+        }
+        s.sync_epoch = s.code_counter + ks;
+        s.nav_sum = s.row19;                                              // L471: correlatorsBuffer[-1]
+        s.nav_count = 1;
+        k = ks + 1;
+    }
+
+    // ---- L471-483: 20 prompts per bit.  Bit j of this call ends at local epoch e_j (exclusive).
+    const int to_first = kMsPerBit - s.nav_count;                         // epochs the pending bit still needs
+    const int avail = n - k;
+    const int nb = (avail >= to_first) ? 1 + (avail - to_first) / kMsPerBit : 0;
+    for (int b0 = 0; b0 < nb; b0 += 32) {
+        const int j = b0 + lane;
+        if (j < nb) {
+            double sum = (j == 0) ? s.nav_sum : 0.0;
+            const int lo = (j == 0) ? k : k + to_first + (j - 1) * kMsPerBit;
+            const int cnt = (j == 0) ? to_first : kMsPerBit;
+            for (int u = 0; u < cnt; ++u) sum += ip(lo + u);              // same order as navPromptSum +=
+            if (j < max_bits) {
+                bits[(long long)ch * max_bits + j] = (sum > 0.0) ? 1 : 0; // Prompt2Bit, decoding.py:27
+                if (bit_sums) bit_sums[(long long)ch * max_bits + j] = sum;
+            }
+        }
+    }
+    produced = min(nb, max_bits);
+    // the bit still being accumulated when the records end
+    int rest_lo = k, rest_cnt = avail;
+    double rest = s.nav_sum;
+    if (nb > 0) {
+        rest_lo = k + to_first + (nb - 1) * kMsPerBit;
+        rest_cnt = n - rest_lo;
+        rest = 0.0;
+        s.nav_count = 0;
+    }
+    if (lane == 0) {
+        for (int u = 0; u < rest_cnt; ++u) rest += ip(rest_lo + u);
+        s.nav_sum = rest;
+        s.nav_count += rest_cnt;
+        s.n_bits += nb;
+        if (n > 0) s.prev_iprompt = ip(n - 1);
+        s.code_counter += n;
+        nav[ch] = s;
+        nbits_out[ch] = produced;
+    }
+}
+
+}  // namespace sydr
+
+using namespace sydr;
+
+extern "C" {
+
+int sydr_nav_state_init(sydr_nav_state* h_state) {
+    SYDR_REQUIRE(h_state != nullptr, SYDR_ERR_ARG, "state pointer is NULL");
+    memset(h_state, 0, sizeof(*h_state));
+    h_state->sync_epoch = -1;
+    return SYDR_OK;
+}
+
+int sydr_nav_bits(const sydr_trk_epoch* d_epochs, int max_epochs, const int* d_nepochs, int first_epoch,
+                  sydr_nav_state* d_nav, int n_channels, signed char* d_bits, double* d_bit_sums, int max_bits,
+                  int* d_nbits, void* stream) {
+    SYDR_REQUIRE(d_epochs && d_nepochs && d_nav && d_bits && d_nbits, SYDR_ERR_ARG, "NULL pointer");
+    SYDR_REQUIRE(max_epochs > 0 && max_bits > 0 && first_epoch >= 0, SYDR_ERR_ARG, "sizes must be positive");
+    if (n_channels <= 0) return SYDR_OK;
+    nav_bits_kernel<<<n_channels, 32, 0, (cudaStream_t)stream>>>(d_epochs, max_epochs, d_nepochs, first_epoch, d_nav,
+                                                                 reinterpret_cast<int8_t*>(d_bits), d_bit_sums,
+                                                                 max_bits, d_nbits);
+    count_launch();
+    SYDR_CUDA_CHECK(cudaGetLastError());
+    return SYDR_OK;
+}
+
+}  // extern "C"

@@ -304,3 +304,53 @@ def epl_batch(iq_dev: torch.Tensor, fs: float, args: np.ndarray, stream=None) ->
     L.check(L.load().sydr_epl_batch(iq_dev.data_ptr(), iq_code(iq_dev), n_complex_samples(iq_dev), float(fs),
                                     d_args.data_ptr(), len(a), d_out.data_ptr(), _stream_ptr(stream)), "sydr_epl_batch")
     return d_out.cpu().numpy().reshape(len(a), 6)
+
+
+# ======================================================================================
+class NavBitEngine:
+    """Bit synchronisation + 20-epoch prompt sums -> navigation bits on the device (K-NAV).
+
+    Consumes the per-epoch records a TrackingEngine leaves in HBM and keeps, per channel, the
+    state ChannelL1CA keeps between ticks (channel_l1ca_borre.py:398-413, 455-491), so only
+    50 bit/s per channel have to cross PCIe.  Records may arrive in pieces of any length."""
+
+    def __init__(self, n_channels: int, max_bits: int = 4096, device=None):
+        L.require_device()
+        if device is not None:
+            torch.cuda.set_device(device)
+        self.device = torch.device("cuda", torch.cuda.current_device())
+        self.n_ch, self.max_bits = int(n_channels), int(max_bits)
+        self._state = torch.empty(self.n_ch * L.NAV_STATE_DTYPE.itemsize, dtype=torch.uint8, device=self.device)
+        self._bits = torch.zeros(self.n_ch * self.max_bits, dtype=torch.int8, device=self.device)
+        self._sums = torch.zeros(self.n_ch * self.max_bits, dtype=torch.float64, device=self.device)
+        self._nbits = torch.zeros(self.n_ch, dtype=torch.int32, device=self.device)
+        self.reset()
+
+    def reset(self):
+        st = np.zeros(1, dtype=L.NAV_STATE_DTYPE)
+        L.check(L.load().sydr_nav_state_init(st.ctypes.data), "sydr_nav_state_init")
+        self._state.copy_(torch.from_numpy(np.repeat(st, self.n_ch).view(np.uint8).reshape(-1)))
+
+    def launch_records(self, d_epochs: torch.Tensor, max_epochs: int, d_nepochs: torch.Tensor, first_epoch=0,
+                       stream=None):
+        """d_epochs: device bytes of [n_ch][max_epochs] sydr_trk_epoch; d_nepochs: int32 [n_ch]."""
+        L.check(L.load().sydr_nav_bits(d_epochs.data_ptr(), int(max_epochs), d_nepochs.data_ptr(), int(first_epoch),
+                                       self._state.data_ptr(), self.n_ch, self._bits.data_ptr(),
+                                       self._sums.data_ptr(), self.max_bits, self._nbits.data_ptr(),
+                                       _stream_ptr(stream)), "sydr_nav_bits")
+
+    def launch(self, trk: "TrackingEngine", first_epoch=0, stream=None):
+        """Consume records [first_epoch, n) of every channel of `trk` (enqueue after trk.launch)."""
+        assert trk.n_ch == self.n_ch
+        self.launch_records(trk._out, trk.max_epochs, trk._nep, first_epoch, stream)
+
+    def states(self) -> np.ndarray:
+        return self._state.cpu().numpy().view(L.NAV_STATE_DTYPE).copy()
+
+    def fetch(self, want_sums=True):
+        """Bits (and sums) produced by the last launch: list of (int8 array, float64 array) per channel."""
+        nb = self._nbits.cpu().numpy()
+        mx = int(nb.max()) if len(nb) else 0
+        bits = self._bits.view(self.n_ch, self.max_bits)[:, :mx].cpu().numpy()
+        sums = self._sums.view(self.n_ch, self.max_bits)[:, :mx].cpu().numpy() if want_sums else None
+        return [(bits[c, :nb[c]].copy(), sums[c, :nb[c]].copy() if want_sums else None) for c in range(self.n_ch)]

@@ -143,6 +143,20 @@ def generate_iq(sc: Scenario, chunk: int = 1 << 20) -> np.ndarray:
     return out
 
 
+def nav_bits_of(sc: Scenario) -> dict:
+    """The +-1 data bits generate_iq modulates on every satellite (same generator, same draws)."""
+    rng = np.random.default_rng(sc.seed + 7919)
+    nbits_nav = int(sc.duration * 50) + 3
+    return {s.prn: rng.choice(np.array([-1.0, 1.0]), nbits_nav) for s in sc.sats}
+
+
+def nav_bit_index(sat, t):
+    """Index into nav_bits_of(...)[prn] of the data bit on the air at receiver time t (seconds)."""
+    fcode = CODE_FREQ * (1.0 + sat.doppler / L1_FREQ)
+    chip = np.floor(fcode * np.asarray(t, dtype=np.float64) - sat.delay_chips).astype(np.int64)
+    return np.floor_divide(chip, 20 * CODE_CHIPS) + 1
+
+
 def to_complex(iq: np.ndarray) -> np.ndarray:
     """What RFSignal.readFile returns: I + 1j*Q as complex128 (rfsignal.py:127-130)."""
     return iq[0::2] + 1j * iq[1::2]

@@ -302,6 +302,45 @@ def g_channel(R):
     save("channel.npz", **out)
 
 
+def g_nav(R):
+    """Bit synchronisation and navigation-bit accumulation of the live reference channel
+    (channel_l1ca_borre.py:398-413, 455-491): per tracking epoch the prompt, navPromptSum,
+    navPromptSumCounter, navBitsCounter and BIT_SYNC after the tick; the bits at the end.  Kept
+    below 62 bits so that the preamble search never rewrites navBitsBuffer."""
+    C = ref_import.load_channel()
+    out = {}
+    fs, nbits, seed, ms, prns, ds = 4e6, 8, 27, 1300, (7, 22), 250
+    sc = synth.make_scenario(fs, nbits, ms * 1e-3, prns, seed, float(ds))
+    iq = synth.generate_iq(sc)
+    x = synth.to_complex(iq)
+    acq_cfg = {"doppler_range": "5000", "doppler_steps": str(ds), "coherent_integration": "1",
+               "non_coherent_integration": "10", "threshold": "1.5"}
+    for prn in prns:
+        cfg = {"filepath": "none", "sampling_frequency": str(fs), "is_complex": "true",
+               "intermediate_frequency": "0.0", "data_size": "8"}
+        rf = C.RFSignal(cfg)
+        spm = rf.samplesPerMs
+        buf = C.CircularBuffer(int(fs * 1e-3 * 100), np.complex128)
+        ch = C.ChannelL1CA(0, buf, None, rf, {"ACQUISITION": acq_cfg, "TRACKING": TRK_CFG})
+        ch.setSatellite(prn)
+        rows = []
+        for tick in range(ms):
+            buf.shift(x[tick * spm:(tick + 1) * spm])
+            res = ch._processHandler()
+            for r in res:
+                if r["type"] == C.ChannelMessage.TRACKING_UPDATE:
+                    rows.append([r["i_prompt"], ch.navPromptSum, ch.navPromptSumCounter, ch.navBitsCounter,
+                                 float(bool(ch.trackFlags & C.TrackingFlags.BIT_SYNC))])
+        assert ch.navBitsCounter < 62
+        out[f"epochs_{prn}"] = np.array(rows, dtype=np.float64)
+        out[f"bits_{prn}"] = np.array(ch.navBitsBuffer[:ch.navBitsCounter], dtype=np.int8)
+        print(f"  nav PRN {prn}: {len(rows)} epochs, {ch.navBitsCounter} bits")
+    out["meta"] = np.array([fs, nbits, seed, ms, ds], dtype=np.float64)
+    out["prns"] = np.array(prns)
+    out["sha"] = sha(iq)
+    save("nav.npz", **out)
+
+
 KAPLAN_TRK_CFG = {  # config/channels/channel_GPS_L1CA_kaplan.ini [TRACKING]
     "correlator_epl_wide": "0.5", "correlator_epl_narrow": "0.5", "dll_threshold": "10.0", "dll_damping_ratio": "0.7",
     "dll_noise_bandwidth": "2.0", "dll_loop_gain": "1.0", "dll_pdi": "0.001", "pll_bandwidth_wide": "25.0",
@@ -411,7 +450,7 @@ def main():
     a = ap.parse_args()
     R = ref_import.load()
     groups = {"codes": g_codes, "peaks": g_peaks, "acq": g_acq, "epl": g_epl, "loop": g_loop, "channel": g_channel,
-              "kaplan": g_kaplan,
+              "kaplan": g_kaplan, "nav": g_nav,
               "decoding": g_decoding}
     for name, fn in groups.items():
         if a.only and name not in a.only and not (name == "acq" and any(o in ACQ_CASES for o in a.only)):

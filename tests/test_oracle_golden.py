@@ -123,6 +123,21 @@ REF_SO = os.path.join(H.ROOT, "oracle", "_ref", "tracking.so")
 
 
 @pytest.mark.skipif(not os.path.exists(REF_SO), reason="oracle/_ref/tracking.so not built (needs /root/reference)")
+def test_nav_bit_oracle_matches_reference_channel(golden):
+    """Bit synchronisation + 20-epoch prompt sums: every tick's navPromptSum, counters and flag of
+    the live reference channel, and its final navBitsBuffer."""
+    g = golden("nav.npz")
+    for prn in g["prns"]:
+        ep, bits = g[f"epochs_{prn}"], g[f"bits_{prn}"]
+        o = O.NavBitOracle()
+        for r in ep:
+            o.step(r[0])
+            assert o.nav_sum == r[1] and o.nav_count == r[2] and len(o.bits) == r[3] and float(o.bit_sync) == r[4]
+        assert np.array_equal(np.array(o.bits, dtype=np.int8), bits) and len(bits) >= 50
+    b, s, sync, _ = O.nav_bits(g[f"epochs_{g['prns'][0]}"][:, 0])
+    assert sync > 100 and len(b) == len(s)
+
+
 def test_against_compiled_reference_c(golden):
     """getCorrelator of the reference's own tracking.c (compiled by oracle/Makefile) vs the oracle."""
     lib = ctypes.CDLL(REF_SO)
