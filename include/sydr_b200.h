@@ -185,6 +185,14 @@ typedef struct {
     double  min_tap_gap;    /* smallest distance, in chips, between the chip-boundary positions
                                of two correlators (0 = 0.5, the -0.5/0/+0.5 spacing); sizes
                                the per-thread chunk for the split-sum path                  */
+    int64_t iq_base;        /* with use_iq_base != 0: sample offset of the recording inside
+                               d_iq for this call, overriding the states' iq_base.  May be
+                               negative: a sliding window that holds samples [w0, w0 + len)
+                               of the recording at d_iq passes iq_base = -w0 (w0 a multiple
+                               of 8 samples) and iq_len = w0 + len, so that `cur` and the
+                               records' `start` stay recording-relative (streaming ingest)   */
+    int32_t use_iq_base;
+    int32_t reserved;
 } sydr_trk_config;
 
 /* Closed-loop Borre tracking (runTracking, channel_l1ca_borre.py:333-451: EPL +

@@ -844,6 +844,8 @@ struct TrkParams {
     int use_tma;
     int append;              // records are indexed by the cumulative epoch count
     long long iq_len;        // > 0: overrides the states' iq_len
+    long long iq_base;       // with has_iq_base: overrides the states' iq_base (sliding window, may be negative)
+    int has_iq_base;
     int seg;                 // half-chip segment path allowed (sampling rate fits the instantiation)
     int resume;              // follow-up of a LEAN launch: continue the record rows, serve kNeedGeneral channels
     long long* prof;         // optional [n_channels][16] phase cycle counters of thread 0 (NULL = off)
@@ -1035,6 +1037,7 @@ __global__ void __launch_bounds__(LEAN ? kLeanThreads : kTrkMaxThreads, LEAN ? 3
     if (tid == 0) {
         sh.cfgs = *gst;
         if (P.iq_len > 0) sh.cfgs.iq_len = P.iq_len;
+        if (P.has_iq_base) sh.cfgs.iq_base = P.iq_base;
         sh.rec_base = P.append ? (int)sh.cfgs.epochs_done : (P.resume ? P.nepochs[ch] : 0);
         if (P.resume && sh.cfgs.status == kNeedGeneral) sh.cfgs.status = 0;
         const sydr_trk_state& g = sh.cfgs;
@@ -1473,6 +1476,9 @@ int sydr_trk_run(const void* d_iq, int iq_dtype, long long iq_alloc_samples, dou
     P.use_tma = use_tma;
     P.append = cfg ? (cfg->append != 0) : 0;
     P.iq_len = cfg ? cfg->iq_len : 0;
+    P.has_iq_base = cfg ? (cfg->use_iq_base != 0) : 0;
+    P.iq_base = P.has_iq_base ? cfg->iq_base : 0;
+    SYDR_REQUIRE(!P.has_iq_base || (P.iq_base & 7) == 0, SYDR_ERR_ARG, "cfg.iq_base must be a multiple of 8 samples");
     P.seg = (g_trk_mode == 0) ? 1 : 0;
     P.resume = 0;
     P.prof = g_trk_prof;

@@ -220,7 +220,7 @@ class TrackingEngine:
         self.max_epochs = int(max_epochs)
         st = np.ascontiguousarray(states)
         assert st.dtype == L.TRK_STATE_DTYPE
-        self.cfg = L.TrkConfig(int(cluster), int(threads), 1 if use_tma else 0, 0, 0, min_tap_gap(st["spacing"]))
+        self.cfg = L.TrkConfig(int(cluster), int(threads), 1 if use_tma else 0, 0, 0, min_tap_gap(st["spacing"]), 0, 0, 0)
         self._states = torch.from_numpy(st.view(np.uint8).reshape(-1).copy()).to(self.device)
         self._out = torch.empty(self.n_ch * self.max_epochs * 128, dtype=torch.uint8, device=self.device)
         self._nep = torch.zeros(self.n_ch, dtype=torch.int32, device=self.device)
@@ -241,12 +241,16 @@ class TrackingEngine:
         self.cfg.min_tap_gap = min_tap_gap(st["spacing"])
         self._states.copy_(torch.from_numpy(st.view(np.uint8).reshape(-1)))
 
-    def launch(self, iq_dev: torch.Tensor, stream=None, iq_len: int = 0, append: bool = False):
+    def launch(self, iq_dev: torch.Tensor, stream=None, iq_len: int = 0, append: bool = False, iq_base=None):
         """Enqueue one tracking launch.  iq_len > 0 limits every recording to its first iq_len
-        samples (streaming upload); append=True continues the record arrays of earlier launches."""
+        samples (streaming upload); append=True continues the record arrays of earlier launches;
+        iq_base (a multiple of 8, may be negative) places the recording inside `iq_dev` for this
+        call: a sliding window holding samples [w0, w0 + len) passes iq_base = -w0, iq_len = w0 + len."""
         iq_dev = ensure_padded(iq_dev)
         self.cfg.iq_len = int(iq_len)
         self.cfg.append = 1 if append else 0
+        self.cfg.use_iq_base = 0 if iq_base is None else 1
+        self.cfg.iq_base = 0 if iq_base is None else int(iq_base)
         store_bytes = iq_dev.untyped_storage().nbytes() - iq_dev.storage_offset() * iq_dev.element_size()
         code = iq_code(iq_dev)
         alloc_samples = store_bytes // _IQ_BYTES[code]
