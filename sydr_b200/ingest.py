@@ -37,7 +37,7 @@ class FileChunkReader:
     the GIL), which is what it takes to feed a PCIe 5 x16 link from the page cache."""
 
     def __init__(self, path: str, np_dtype, chunk_samples: int, skip_samples: int = 0, max_samples: int | None = None,
-                 n_buffers: int = 3, threads: int = 4):
+                 n_buffers: int = 3, threads: int = 4, buffers=None, pool=None):
         self.path = path
         self.itemsize = np.dtype(np_dtype).itemsize
         self.bps = 2 * self.itemsize                            # bytes per complex sample
@@ -49,18 +49,25 @@ class FileChunkReader:
         self.skip = int(skip_samples)
         self.n_chunks = -(-self.total // self.chunk) if self.total else 0
         tdt = torch.int8 if self.itemsize == 1 else torch.int16
-        self._bufs = [torch.empty(2 * self.chunk, dtype=tdt, pin_memory=torch.cuda.is_available())
-                      for _ in range(n_buffers)]
+        # pinned staging buffers and the read pool may be handed in by a long-lived owner (page-locking
+        # hundreds of MB costs tens of milliseconds)
+        self._bufs = buffers if buffers is not None else self.alloc_buffers(tdt, self.chunk, n_buffers)
         self._free = queue.Queue()
-        for i in range(n_buffers):
+        for i in range(len(self._bufs)):
             self._free.put(i)
         self._ready = queue.Queue()
         self._threads = max(1, int(threads))
-        self._pool = ThreadPoolExecutor(self._threads)
+        self._own_pool = pool is None
+        self._pool = ThreadPoolExecutor(self._threads) if pool is None else pool
         self._fd = os.open(path, os.O_RDONLY)
         self._stop = False
         self._worker = threading.Thread(target=self._run, daemon=True)
         self._worker.start()
+
+    @staticmethod
+    def alloc_buffers(tdt, chunk_samples: int, n_buffers: int = 3):
+        return [torch.empty(2 * int(chunk_samples), dtype=tdt, pin_memory=torch.cuda.is_available())
+                for _ in range(n_buffers)]
 
     def _read_into(self, view: memoryview, offset: int):
         done = 0
@@ -108,7 +115,8 @@ class FileChunkReader:
         self._stop = True
         self._free.put(None)
         self._worker.join(timeout=5)
-        self._pool.shutdown(wait=False)
+        if self._own_pool:
+            self._pool.shutdown(wait=False)
         os.close(self._fd)
 
 
@@ -122,7 +130,7 @@ class StreamingReceiver:
 
     def __init__(self, rf, search_prns, n_channels, chunk_seconds=1.0, doppler_range=5000.0, doppler_step=250.0,
                  coh=1, noncoh=10, threshold=1.5, channel_cfg=None, want_records=True, want_bits=True,
-                 reader_threads=4, device=None, cluster=0, threads=0, use_tma=True):
+                 reader_threads=8, device=None, cluster=0, threads=0, use_tma=True):
         L.require_device()
         if not rf.isComplex:
             raise L.SydrError("StreamingReceiver needs interleaved I,Q samples (is_complex = true)")
@@ -150,6 +158,8 @@ class StreamingReceiver:
         self._win = [torch.zeros(2 * (self.tail + self.chunk) + pad, dtype=self._tdt, device=self.device)
                      for _ in range(2)]
         self._copy = torch.cuda.Stream(device=self.device)
+        self._host_bufs = FileChunkReader.alloc_buffers(self._tdt, self.chunk, 3)
+        self._pool = ThreadPoolExecutor(max(1, self.reader_threads))
         self._rec_host = [None, None]
         self._nep_host = [torch.zeros(self.n_channels, dtype=torch.int32, pin_memory=True) for _ in range(2)]
         self._trk = None
@@ -158,6 +168,7 @@ class StreamingReceiver:
 
     def close(self):
         self.acq.close()
+        self._pool.shutdown(wait=False)
 
     # ------------------------------------------------------------------------------------
     def _start_tracking(self, peaks):
@@ -170,10 +181,15 @@ class StreamingReceiver:
             chans.append(dict(prn=int(peaks["prn"][i]), carrier_freq=carrier, start_sample=cur, iq_len=0))
         if chans:
             states = make_trk_states(self.fs, chans, self.channel_cfg)
+            n_ch = len(chans)
+            if self._trk is not None and self._trk.n_ch == n_ch:        # a receiver that is run again keeps its buffers
+                self._trk.reset(states)
+                if self._nav is not None:
+                    self._nav.reset()
+                return chans
             self._trk = TrackingEngine(self.fs, states, self.max_epochs, device=self.device, **self.trk_cfg)
             if self.want_bits:
-                self._nav = NavBitEngine(len(chans), max_bits=self.max_epochs // 20 + 2, device=self.device)
-            n_ch = len(chans)
+                self._nav = NavBitEngine(n_ch, max_bits=self.max_epochs // 20 + 2, device=self.device)
             self._rec_host = [torch.empty(n_ch * self.max_epochs * 128, dtype=torch.uint8, pin_memory=True)
                               for _ in range(2)]
         return chans
@@ -197,7 +213,7 @@ class StreamingReceiver:
     def run(self, skip_samples: int = 0, max_samples: int | None = None):
         """Generator over chunks: {'chunk', 'peaks' and 'channels' (first chunk), 'epochs', 'bits', 'nepochs'}."""
         reader = FileChunkReader(self.rf.filepath, self.np_dtype, self.chunk, skip_samples, max_samples,
-                                 threads=self.reader_threads)
+                                 threads=self.reader_threads, buffers=self._host_bufs, pool=self._pool)
         comp = torch.cuda.current_stream()
         T, CH = self.tail, self.chunk
         chans, peaks = None, None
