@@ -106,3 +106,20 @@ def load_channel_kaplan():
     ns.LoopLockState = LoopLockState
     ns.TrackingFlags = TrackingFlags
     return ns
+
+
+def load_database():
+    """The reference's SQLite result sink (sydr/io/database.py) for fixture generation.  Its module
+    imports ``pymap3d`` through sydr/utils/coordinate.py without using it on this path: stubbed."""
+    load()
+    if "pymap3d" not in sys.modules:
+        try:
+            import pymap3d  # noqa: F401
+        except Exception:
+            sys.modules["pymap3d"] = types.ModuleType("pymap3d")
+    ns = types.SimpleNamespace()
+    from sydr.io.database import DatabaseHandler
+    from sydr.utils.enumerations import ChannelMessage
+    ns.DatabaseHandler = DatabaseHandler
+    ns.ChannelMessage = ChannelMessage
+    return ns

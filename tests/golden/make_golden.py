@@ -341,6 +341,68 @@ def g_nav(R):
     save("nav.npz", **out)
 
 
+def db_packets(CM, trk_rows):
+    """Result packets as the channel and the receiver build them (channel_l1ca_borre.py:319-325,
+    432-449; receiver.py:322-396), from the tracking rows of loop.npz.  CM = ChannelMessage enum."""
+    cmap = (np.arange(12, dtype=np.float64).reshape(3, 4) + 0.5)
+    acq = {"cid": 0, "type": CM.ACQUISITION_UPDATE, "carrierFrequency": 1250.0, "codeOffset": 1234,
+           "frequency_idx": 15, "code_idx": 1234, "correlation_map": cmap, "peak_ratio": 3.25,
+           "channel_id": 0, "time": 1000.5, "time_sample": 40000}
+    trk = []
+    for k, r in enumerate(trk_rows):
+        trk.append({"cid": 0, "type": CM.TRACKING_UPDATE,
+                    "i_early": float(r[1]), "q_early": float(r[2]), "i_prompt": float(r[3]), "q_prompt": float(r[4]),
+                    "i_late": float(r[5]), "q_late": float(r[6]), "dll": float(r[7]), "pll": float(r[8]), "fll": 0.0,
+                    "carrier_frequency": float(r[9]), "code_frequency": float(r[10]),
+                    "cn0": 0.0 if (k % 20 == 19) else float("nan"), "pll_lock": 0.0, "fll_lock": 0.0, "lock_state": 0,
+                    "carrier_frequency_error": float(r[11]), "code_frequency_error": float(r[12]),
+                    "channel_id": 0, "time": 1000.5 + 0.001 * k, "time_sample": 44000 + 4000 * k})
+    dec = {"cid": 0, "type": CM.DECODING_UPDATE, "subframe_id": 2, "tow": 345600, "bits": "0110" * 75,
+           "channel_id": 0, "time": 1007.0, "time_sample": 26000000}
+    chan = {"id": 0, "physical_id": 0, "system": "GPS", "satellite_id": 3, "signal": "GPS_L1_CA",
+            "start_time": 1000.0, "start_sample": 0}
+    return acq, trk, dec, chan
+
+
+def db_dump(db):
+    """Schema and rows of every table a channel writes to; BLOBs unpickled, NaN/NULL as None."""
+    out = {}
+    for table in ("channel", "acquisition", "tracking", "decoding"):
+        info = db.cursor.execute(f"PRAGMA table_info({table})").fetchall()
+        rows = db.sqlRequest(f"SELECT * FROM {table};")
+        clean = []
+        for r in rows:
+            clean.append({k: (np.asarray(v).tolist() if isinstance(v, (list, np.ndarray)) else v) for k, v in r.items()})
+        out[table] = {"schema": [[c[1], c[2], c[5]] for c in info], "rows": clean}
+    return out
+
+
+def g_database(R):
+    """The reference's own DatabaseHandler (sydr/io/database.py) fed with channel packets: schema and
+    rows of the resulting SQLite file."""
+    import json
+    import tempfile
+    D = ref_import.load_database()
+    loop = np.load(os.path.join(HERE, "loop.npz"))
+    acq, trk, dec, chan = db_packets(D.ChannelMessage, loop["fs4_trk_3"][:60])
+    with tempfile.TemporaryDirectory() as tmp:
+        db = D.DatabaseHandler(os.path.join(tmp, "ref.db"), overwrite=True)
+        db.addData("channel", chan)
+        db.addData("acquisition", acq)
+        for p in trk[:25]:
+            db.addData("tracking", p)
+        db.commit()
+        db.addData("decoding", dec)
+        for p in trk[25:]:
+            db.addData("tracking", p)
+        db.commit()
+        dump = db_dump(db)
+        db.close()
+    with open(os.path.join(HERE, "database.json"), "w") as f:
+        json.dump(dump, f)
+    print(f"  wrote database.json ({len(dump['tracking']['rows'])} tracking rows)")
+
+
 KAPLAN_TRK_CFG = {  # config/channels/channel_GPS_L1CA_kaplan.ini [TRACKING]
     "correlator_epl_wide": "0.5", "correlator_epl_narrow": "0.5", "dll_threshold": "10.0", "dll_damping_ratio": "0.7",
     "dll_noise_bandwidth": "2.0", "dll_loop_gain": "1.0", "dll_pdi": "0.001", "pll_bandwidth_wide": "25.0",
@@ -450,7 +512,7 @@ def main():
     a = ap.parse_args()
     R = ref_import.load()
     groups = {"codes": g_codes, "peaks": g_peaks, "acq": g_acq, "epl": g_epl, "loop": g_loop, "channel": g_channel,
-              "kaplan": g_kaplan, "nav": g_nav,
+              "kaplan": g_kaplan, "nav": g_nav, "database": g_database,
               "decoding": g_decoding}
     for name, fn in groups.items():
         if a.only and name not in a.only and not (name == "acq" and any(o in ACQ_CASES for o in a.only)):

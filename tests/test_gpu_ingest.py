@@ -77,3 +77,40 @@ def test_streaming_bits_only_and_skip(tmp_path):
         assert a["states"][c].tobytes() == b["states"][c].tobytes()
         last = a["epochs"][c][-1]
         assert last["start"] + last["n"] <= span and last["start"] + 2 * last["n"] > span - 8
+
+
+def test_file_to_database(tmp_path):
+    """File -> StreamingReceiver -> SQLite in the reference's format: every epoch is a row whose
+    values are the device records; cn0 follows the bit-sync rule; time_sample is the emitting tick."""
+    from sydr_b200 import synth
+    from sydr_b200.ingest import StreamingReceiver
+    from sydr_b200.io.database import DatabaseHandler
+    fs, nbits = 4e6, 8
+    sc = synth.make_scenario(fs, nbits, 0.6, (7, 22), 93, 250.0)
+    path = str(tmp_path / "rec.bin")
+    synth.write_file(path, synth.generate_iq(sc))
+    rx = StreamingReceiver(_rf(path, fs, nbits), [7, 22, 9], 4, chunk_seconds=0.13)
+    ref = rx.run_all()
+    db = DatabaseHandler(str(tmp_path / "out.db"), overwrite=True)
+    tot = rx.run_to_database(db, wall_time=lambda: 123.0)
+    sync = rx._nav.states()["sync_epoch"]
+    rx.close()
+    assert tot["tracking_rows"] == sum(len(e) for e in ref["epochs"])
+    assert [r["satellite_id"] for r in db.fetchTable("channel")] == [7, 22]
+    acq = db.fetchAcquisition()
+    assert [a["code_idx"] for a in acq] == [int(ref["peaks"][ref["peaks"]["prn"] == p]["code_idx"][0]) for p in (7, 22)]
+    for cid in range(2):
+        rows = db.fetchTracking(cid)
+        e = ref["epochs"][cid]
+        assert len(rows) == len(e) > 550
+        assert [r["i_prompt"] for r in rows] == e["corr"][:, 2].tolist()
+        assert [r["carrier_frequency"] for r in rows] == e["carrier_freq"].tolist()
+        assert [r["code_frequency_error"] for r in rows] == e["code_err"].tolist()
+        ts = np.array([r["time_sample"] for r in rows])
+        end = e["start"] + e["n"]
+        assert (ts % 4000 == 0).all() and (ts >= end).all() and (ts - end < 4000).all()
+        s = int(sync[cid])
+        zero = [k for k, r in enumerate(rows) if r["cn0"] == 0.0]
+        assert s > 100 and zero == list(range(s + 20, len(rows), 20))
+        assert all(r["cn0"] is None for k, r in enumerate(rows) if k not in zero)       # NaN is stored as NULL
+    db.close()
