@@ -229,6 +229,15 @@ __device__ __forceinline__ void st_async_v4(uint32_t dst_cluster_addr, uint32_t 
         : "memory");
 }
 
+__device__ __forceinline__ void st_async_v4u(uint32_t dst_cluster_addr, uint32_t bar_cluster_addr, uint32_t a, uint32_t b,
+                                             uint32_t c, uint32_t d) {
+    asm volatile(
+        "st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];" ::
+            "r"(dst_cluster_addr),
+        "r"(a), "r"(b), "r"(c), "r"(d), "r"(bar_cluster_addr)
+        : "memory");
+}
+
 // Remote (DSMEM) 4-byte store, complete_tx(4) on the destination CTA's mbarrier.
 __device__ __forceinline__ void st_async_b32(uint32_t dst_cluster_addr, uint32_t bar_cluster_addr, float a) {
     asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];" ::"r"(dst_cluster_addr),

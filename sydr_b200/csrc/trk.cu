@@ -847,6 +847,8 @@ struct TrkParams {
     long long iq_base;       // with has_iq_base: overrides the states' iq_base (sliding window, may be negative)
     int has_iq_base;
     int seg;                 // half-chip segment path allowed (sampling rate fits the instantiation)
+    float acc_scale;         // integer IQ: power of two that takes a warp's correlator sums into int32 (fixed-point all-reduce)
+    double acc_inv;          // 1 / acc_scale
     int resume;              // follow-up of a LEAN launch: continue the record rows, serve kNeedGeneral channels
     long long* prof;         // optional [n_channels][16] phase cycle counters of thread 0 (NULL = off)
 };
@@ -933,6 +935,40 @@ __device__ __forceinline__ double gather_total(const SH& sh, int slot, int n_ent
     return s;
 }
 
+// acc + (int64)v in one instruction (sign extension and the 64-bit carry chain folded into IMAD.WIDE).
+__device__ __forceinline__ long long mad_wide(int v, long long acc) {
+    long long r;
+    int one;
+    asm("mov.s32 %0, 1;" : "=r"(one));
+    asm("mad.wide.s32 %0, %1, %2, %3;" : "=l"(r) : "r"(v), "r"(one), "l"(acc));
+    return r;
+}
+
+// The same for the fixed-point exchange (integer IQ): entries are int32[8] warp totals scaled by a
+// power of two; integer addition is associative, so the total does not depend on the order, the
+// cluster shape or the warp count.  All loads are issued before the first addition.
+template <int K, class SH>      // K entries per lane and pass (a lane walks entries lane/8, lane/8 + 4, ...)
+__device__ __forceinline__ double gather_total_fixed(const SH& sh, int slot, int n_ent, int lane, double inv_scale) {
+    const int c = lane & 7;
+    const int* g = reinterpret_cast<const int*>(&sh.gather[slot][0][0]) + c;
+    long long s = 0;
+    for (int base = lane >> 3; base < n_ent; base += 4 * K) {
+        int v[K];
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const int i = base + 4 * k;
+            v[k] = (i < n_ent) ? g[i * 8] : 0;
+        }
+        long long a0 = 0, a1 = 0;
+#pragma unroll
+        for (int k = 0; k < K; k += 2) { a0 = mad_wide(v[k], a0); a1 = mad_wide(v[k + 1], a1); }   // one IMAD.WIDE per entry
+        s += a0 + a1;
+    }
+    s += __shfl_xor_sync(0xffffffffu, s, 8);
+    s += __shfl_xor_sync(0xffffffffu, s, 16);
+    return (double)s * inv_scale;
+}
+
 // Warp 0: close the CODE loop of epoch e (DLL_NNEML + Borre filter + code NCO,
 // channel_l1ca_borre.py:383-388, 422-429), store its share of the epoch record.
 template <class SH>
@@ -1016,12 +1052,18 @@ __device__ __forceinline__ void carrier_close(SH& sh, CarrierState& st, double c
 // three channels share an SM and one channel's loop closure hides behind the others' correlation.
 // An epoch the segment path cannot serve stops the channel with status kNeedGeneral; the host
 // then repeats the launch with the general instantiation (sydr_trk_run).
-template <int DT, int VPC, bool TMA, bool LEAN>
+// PROF = phase cycle counters compiled in (diagnostics instantiation; the counters sit on the serial
+// chain, so the production instantiation does not carry them).
+template <int DT, int VPC, bool TMA, bool LEAN, bool PROF = false>
 __global__ void __launch_bounds__(LEAN ? kLeanThreads : kTrkMaxThreads, LEAN ? 3 : 1) trk_borre_kernel(const TrkParams P) {
     constexpr int SPV = IqTraits<DT>::SPV, BPS = IqTraits<DT>::BPS;
     constexpr int C = SPV * VPC;
     extern __shared__ __align__(128) uint8_t dyn_smem[];
     constexpr int NV = SegTraits<DT, VPC>::NV;
+    // Integer IQ: the correlator sums of a warp are bounded, so they are exchanged in fixed point
+    // (one REDUX per component instead of a shuffle tree, 32 B instead of 64 B per warp and CTA,
+    // order-independent integer totals).  complex64 input has no bound: FP32 tree + FP64 totals.
+    constexpr bool FIX = (DT != SYDR_IQ_F32);
     __shared__ __align__(16) TrkSharedT<(LEAN ? kLeanThreads / 32 : kMaxCluster * kTrkMaxWarps), (NV > 0 ? kSegTab : 1)> sh;
     const unsigned full = 0xffffffffu;
 
@@ -1071,7 +1113,7 @@ __global__ void __launch_bounds__(LEAN ? kLeanThreads : kTrkMaxThreads, LEAN ? 3
     const long long rec_alloc = P.iq_alloc - sh.cfgs.iq_base;   // samples readable from rec_base
     sydr_trk_epoch* out_row = (rank == 0) ? P.out + (long long)ch * P.max_epochs + sh.rec_base : nullptr;
 
-    const bool prof = (P.prof != nullptr) && tid == 0;
+    const bool prof = PROF && (P.prof != nullptr) && tid == 0;
 #define SYDR_TICK(k)                                   \
     if (prof) {                                        \
         const long long now__ = clock64();             \
@@ -1079,7 +1121,7 @@ __global__ void __launch_bounds__(LEAN ? kLeanThreads : kTrkMaxThreads, LEAN ? 3
         sh.tprev = now__;                              \
     }
     if (prof) sh.tprev = clock64();
-    const bool prof1 = (P.prof != nullptr) && tid == 32;   // carrier warp: slots 10..13
+    const bool prof1 = PROF && (P.prof != nullptr) && tid == 32;   // carrier warp: slots 10..13
 #define SYDR_TICK1(k)                                  \
     if (prof1) {                                       \
         const long long now__ = clock64();             \
@@ -1145,7 +1187,7 @@ __global__ void __launch_bounds__(LEAN ? kLeanThreads : kTrkMaxThreads, LEAN ? 3
                     sh.ctl.ec.fast = fast;
                     sh.ctl.a = sc.cur;
                     sh.n_hist[epoch & 1] = sc.n_req;
-                    if (S > 1) mbar_arrive_expect_tx(&sh.bar_gather[epoch & 1], 64u * (uint32_t)n_ent);   // arm this epoch's gather
+                    if (S > 1) mbar_arrive_expect_tx(&sh.bar_gather[epoch & 1], (FIX ? 32u : 64u) * (uint32_t)n_ent);   // arm this epoch's gather
                 }
             }
             if (lane == 5) { sh.ctl.stop = stop; sh.status = status; }
@@ -1219,10 +1261,31 @@ __global__ void __launch_bounds__(LEAN ? kLeanThreads : kTrkMaxThreads, LEAN ? 3
             }
         }
         SYDR_TICK(3)                                   // correlate (thread 0's chunks)
-        acc[6] = err ? 1.f : 0.f;                      // code-index overflow anywhere aborts the channel
-        const float wsum = warp_sum8(acc, lane);       // lane L: warp total of component sum8_index(L)
         const int slot = epoch & 1;
-        {
+        if (FIX) {
+            // every lane ends up with the six warp totals; lanes 2r and 2r+1 send the two 16-byte
+            // halves of the warp's entry to CTA r
+            int q[6];
+#pragma unroll
+            for (int k = 0; k < 6; ++k) q[k] = __reduce_add_sync(full, __float2int_rn(acc[k] * P.acc_scale));
+            const int eflag = __any_sync(full, err) ? 1 : 0;       // code-index overflow anywhere aborts the channel
+            const int hi = lane & 1;
+            const uint32_t v0 = (uint32_t)(hi ? q[4] : q[0]), v1 = (uint32_t)(hi ? q[5] : q[1]);
+            const uint32_t v2 = (uint32_t)(hi ? eflag : q[2]), v3 = (uint32_t)(hi ? 0 : q[3]);
+            int* dst = reinterpret_cast<int*>(&sh.gather[slot][0][0]) + (rank * W + warp) * 8 + hi * 4;
+            if (S > 1) {
+                if (lane < 2 * (int)S) {
+                    const uint32_t r = (uint32_t)lane >> 1;
+                    st_async_v4u(mapa_u32(smem_u32(dst), r), mapa_u32(smem_u32(&sh.bar_gather[slot]), r), v0, v1, v2, v3);
+                }
+            } else {
+                if (lane < 2) *reinterpret_cast<uint4*>(dst) = make_uint4(v0, v1, v2, v3);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&sh.bar_gather[slot]);
+            }
+        } else {
+            acc[6] = err ? 1.f : 0.f;
+            const float wsum = warp_sum8(acc, lane);   // lane L: warp total of component sum8_index(L)
             const int c = sum8_index(lane);
             double* dst = &sh.gather[slot][rank * W + warp][c];
             const double wd = (double)wsum;            // the only float -> double conversion of the epoch
@@ -1244,7 +1307,7 @@ __global__ void __launch_bounds__(LEAN ? kLeanThreads : kTrkMaxThreads, LEAN ? 3
             mbar_wait(&sh.bar_gather[slot], (e >> 1) & 1);       // st.async data is visible once the phase completes
             SYDR_TICK(5)                               // all-gather: wait for the slowest warp of the cluster
             SYDR_TICK1(10)                             // carrier warp: everything up to the gather
-            const double ck = gather_total(sh, slot, n_ent, lane);
+            const double ck = FIX ? gather_total_fixed<(LEAN ? 2 : 18)>(sh, slot, n_ent, lane, P.acc_inv) : gather_total(sh, slot, n_ent, lane);
             SYDR_TICK(7)                               // totals
             SYDR_TICK1(11)
             sydr_trk_epoch* rec = out_row ? out_row + e : nullptr;
@@ -1303,6 +1366,7 @@ int launch_trk(const TrkParams& P, int n_channels, int cluster, int threads, int
                  "tracking window needs %zu B of shared memory; raise cfg.cluster", smem);
     constexpr bool HAS_LEAN = SegTraits<DT, VPC>::NV > 0;
     auto kern = P.use_tma ? trk_borre_kernel<DT, VPC, true, false> : trk_borre_kernel<DT, VPC, false, false>;
+    if (P.prof != nullptr) kern = P.use_tma ? trk_borre_kernel<DT, VPC, true, false, true> : trk_borre_kernel<DT, VPC, false, false, true>;
     size_t smem_launch = smem;
     if constexpr (HAS_LEAN) {
         if (lean) {
@@ -1480,6 +1544,17 @@ int sydr_trk_run(const void* d_iq, int iq_dtype, long long iq_alloc_samples, dou
     P.iq_base = P.has_iq_base ? cfg->iq_base : 0;
     SYDR_REQUIRE(!P.has_iq_base || (P.iq_base & 7) == 0, SYDR_ERR_ARG, "cfg.iq_base must be a multiple of 8 samples");
     P.seg = (g_trk_mode == 0) ? 1 : 0;
+    // Fixed-point exchange: |warp total| <= samples the warp handles x the largest sample magnitude.
+    // A warp never handles more than twice its even share of the longest epoch (+ edge segments);
+    // the scale is the largest power of two that keeps that bound inside int32.
+    auto set_scale = [&](TrkParams& Q_, int warps) {
+        const double per_warp = 2.0 * (double)n_max / (double)(warps < 1 ? 1 : warps) + 128.0;
+        const double maxmag = (iq_dtype == SYDR_IQ_I8) ? 182.0 : 46342.0;      // |I + jQ| of a full-scale sample
+        int k = (int)floor(log2(2147483647.0 / (per_warp * maxmag * 1.01)));
+        if (k > 20) k = 20;
+        Q_.acc_scale = (float)ldexp(1.0, k);
+        Q_.acc_inv = ldexp(1.0, -k);
+    };
     P.resume = 0;
     P.prof = g_trk_prof;
     cudaStream_t s = (cudaStream_t)stream;
@@ -1487,6 +1562,7 @@ int sydr_trk_run(const void* d_iq, int iq_dtype, long long iq_alloc_samples, dou
         TrkParams PL = P;
         PL.use_tma = 0;
         const int lt = (!auto_shape && threads > 0) ? threads : kLeanThreads;
+        set_scale(PL, lt / 32);
         const int rc2 = dispatch_trk(iq_dtype, vpc, PL, n_channels, 1, lt, 1, s);
         if (rc2 != SYDR_OK) return rc2;
         // The general instantiation follows on the same stream: channels the LEAN kernel finished
@@ -1494,6 +1570,7 @@ int sydr_trk_run(const void* d_iq, int iq_dtype, long long iq_alloc_samples, dou
         P.resume = 1;
         if (auto_shape) threads = kTrkMaxThreads;
     }
+    set_scale(P, cluster * (threads / 32));
     return dispatch_trk(iq_dtype, vpc, P, n_channels, cluster, threads, 0, s);
 }
 
