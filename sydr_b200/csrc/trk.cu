@@ -971,9 +971,19 @@ __device__ __forceinline__ double gather_total_fixed(const SH& sh, int slot, int
 
 // Warp 0: close the CODE loop of epoch e (DLL_NNEML + Borre filter + code NCO,
 // channel_l1ca_borre.py:383-388, 422-429), store its share of the epoch record.
+// The part of the code-loop update that does not need the correlator sums (evaluated while the
+// all-gather is still in flight): epoch length as a double and the advanced code phase, L424.
+struct CodePre { double n, rem_code; };
+__device__ __forceinline__ CodePre code_pre(const CodeState& st) {
+    CodePre p;
+    p.n = i2d(st.n_req);
+    p.rem_code = dadd(st.rem_code, dsub(dmul(p.n, st.code_step), (double)kCodeChips));   // L424
+    return p;
+}
+
 template <class SH>
 __device__ __forceinline__ void code_close(SH& sh, CodeState& st, int& status, double ck, sydr_trk_epoch* rec,
-                                           int lane) {
+                                           int lane, const CodePre& pre) {
     const unsigned full = 0xffffffffu;
     // |E| (even lanes) and |L| (odd lanes)                                    tracking.py:126
     const double mx = __shfl_sync(full, ck, (lane & 1) ? 4 : 0), my = __shfl_sync(full, ck, (lane & 1) ? 5 : 1);
@@ -984,9 +994,9 @@ __device__ __forceinline__ void code_close(SH& sh, CodeState& st, int& status, d
     double nco_code = dmul(sh.K.dll_c1, dsub(code_err, st.nco_code_err));       // BorreLoopFilter
     nco_code = dadd(nco_code, dmul(sh.K.dll_c2, code_err));
     const long long e_start = st.cur;
-    const double n = i2d(st.n_req);
+    const double n = pre.n;
     st.code_freq = dsub(st.code_freq, nco_code);                                 // L422
-    st.rem_code = dadd(st.rem_code, dsub(dmul(n, st.code_step), (double)kCodeChips));   // L424
+    st.rem_code = pre.rem_code;                                                  // L424
     st.code_step = ddiv_by(st.code_freq, sh.K.fs, sh.K.inv_fs);                  // L425
     st.cur += st.n_req;                                                          // L428
     st.inv_step = newton_rcp(st.code_step, st.inv_step);                         // the step moved by ~1e-9
@@ -1008,21 +1018,26 @@ __device__ __forceinline__ void code_close(SH& sh, CodeState& st, int& status, d
 
 // Warp 1: close the CARRIER loop of epoch e (remaining carrier phase, PLL_costa + Borre filter +
 // carrier NCO, channel_l1ca_borre.py:364-365, 391-396, 423), store its share of the record.
+// The remaining carrier phase after the epoch does not depend on the correlator sums either
+// (L364-365, the old carrier frequency): evaluated while the all-gather is in flight.
 template <class SH>
-__device__ __forceinline__ void carrier_close(SH& sh, CarrierState& st, double ck, int n_epoch,
-                                              sydr_trk_epoch* rec, int lane) {
-    const unsigned full = 0xffffffffu;
-    const double ip = __shfl_sync(full, ck, 2), qp = __shfl_sync(full, ck, 3);
+__device__ __forceinline__ double carrier_pre(const SH& sh, const CarrierState& st, int n_epoch) {
     const double n = i2d(n_epoch);
     // L364-365: rem' = (rem - ((fc*2)*pi*n)/fs) mod 2 pi   (Python float %: result in [0, 2 pi))
     const double twopi = 2.0 * kPi;
     double rc = dsub(st.rem_carrier, ddiv_by(dmul(dmul(dmul(st.carrier_freq, 2.0), kPi), n), sh.K.fs, sh.K.inv_fs));
-    {
-        const double q = floor(rc * 0.15915494309189535);
-        rc = fma(-q, twopi, rc);
-        if (rc < 0.0) rc += twopi;
-        if (rc >= twopi) rc -= twopi;
-    }
+    const double q = floor(rc * 0.15915494309189535);
+    rc = fma(-q, twopi, rc);
+    if (rc < 0.0) rc += twopi;
+    if (rc >= twopi) rc -= twopi;
+    return rc;
+}
+
+template <class SH>
+__device__ __forceinline__ void carrier_close(SH& sh, CarrierState& st, double ck, double rc,
+                                              sydr_trk_epoch* rec, int lane) {
+    const unsigned full = 0xffffffffu;
+    const double ip = __shfl_sync(full, ck, 2), qp = __shfl_sync(full, ck, 3);
     st.rem_carrier = rc;
     const double ph_err = ddiv_by(atan(ddiv(qp, ip)), kGpsPi * 2.0, 1.0 / (kGpsPi * 2.0));   // PLL_costa
     double nco_car = dmul(sh.K.pll_c1, dsub(ph_err, st.nco_carrier_err));        // BorreLoopFilter
@@ -1135,11 +1150,16 @@ __global__ void __launch_bounds__(LEAN ? kLeanThreads : kTrkMaxThreads, LEAN ? 3
     CarrierState sk = sh.sk;
     int status = sh.cfgs.status;                   // != 0: aborted earlier (< 0) or idle slot (> 0): no epochs
     int epoch = 0;
+    // loop-invariant limits of the stop test
+    const long long cap64 = (long long)S * Q * C - SPV;
+    const unsigned n_cap = (unsigned)(cap64 < 0 ? 0 : (cap64 > 0x7fffffffLL ? 0x7fffffffLL : cap64));
+    const int epoch_cap = P.max_epochs - sh.rec_base;
+    const long long iq_len_reg = sh.cfgs.iq_len;
     while (true) {
         // ---- (C, second half) publish the constants of epoch `epoch`
         if (warp == 0) {
-            if (sc.n_req <= 0 || (long long)sc.n_req + SPV > (long long)S * Q * C) status = SYDR_ERR_STATE;
-            bool stop = (status != 0) || (sh.rec_base + epoch >= P.max_epochs) || (sc.cur + sc.n_req > sh.cfgs.iq_len);
+            if ((unsigned)(sc.n_req - 1) >= n_cap) status = SYDR_ERR_STATE;       // n_req <= 0 or beyond the staged window
+            bool stop = (status != 0) || (epoch >= epoch_cap) || (sc.cur + sc.n_req > iq_len_reg);
             double t_start = 0.0, t_step = 0.0, t_stop = 0.0;
             int fast = 0, seg = 0, hb = 0, rounds = 0;
             if (!stop) {
@@ -1304,6 +1324,11 @@ __global__ void __launch_bounds__(LEAN ? kLeanThreads : kTrkMaxThreads, LEAN ? 3
         ++epoch;
         // ---- (C) close the loops of epoch e
         if (warp < 2) {
+            // what the loop updates need besides the sums, while the all-gather is in flight
+            CodePre cpre = {0.0, 0.0};
+            double rc_next = 0.0;
+            if (warp == 0) cpre = code_pre(sc);
+            else rc_next = carrier_pre(sh, sk, sh.n_hist[e & 1]);
             mbar_wait(&sh.bar_gather[slot], (e >> 1) & 1);       // st.async data is visible once the phase completes
             SYDR_TICK(5)                               // all-gather: wait for the slowest warp of the cluster
             SYDR_TICK1(10)                             // carrier warp: everything up to the gather
@@ -1311,8 +1336,8 @@ __global__ void __launch_bounds__(LEAN ? kLeanThreads : kTrkMaxThreads, LEAN ? 3
             SYDR_TICK(7)                               // totals
             SYDR_TICK1(11)
             sydr_trk_epoch* rec = out_row ? out_row + e : nullptr;
-            if (warp == 0) code_close(sh, sc, status, ck, rec, lane);
-            else carrier_close(sh, sk, ck, sh.n_hist[e & 1], rec, lane);
+            if (warp == 0) code_close(sh, sc, status, ck, rec, lane, cpre);
+            else carrier_close(sh, sk, ck, rc_next, rec, lane);
             SYDR_TICK(6)                               // loop closure
             SYDR_TICK1(12)
         }
