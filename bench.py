@@ -397,24 +397,11 @@ def main():
     k_ev = []
     ev[0].record()
     for _ in range(args.steps):
-        a0, a1, t1 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
-        a0.record()
-        pipe.acq.launch(d_iq)
-        a1.record()
-        peaks = pipe.acq.fetch()["peaks"]
-        sel = pipe.select_channels(peaks)
-        from sydr_b200.engine import make_trk_states
-        chans = [dict(prn=int(peaks["prn"][i]), carrier_freq=pipe.acq.handoff(peaks[i])[0],
-                      start_sample=pipe.acq.handoff(peaks[i])[2], iq_len=chunk_samples) for i in sel]
-        st = make_trk_states(FS, chans)
-        pipe._trk.reset(st)
-        t0 = torch.cuda.Event(enable_timing=True)
-        t0.record()
-        pipe._trk.launch(d_iq)
-        t1.record()
+        marks = []
+        pipe.process_device(d_iq, marks)                # acquisition, K-HAND, tracking: enqueued back to back
         if world > 1:
             dist.all_gather_into_tensor(gathered, pipe.acq.peaks_device())
-        k_ev.append((a0, a1, t0, t1))
+        k_ev.append(tuple(marks))
     ev[1].record()
     barrier()
     launches = int(lib.sydr_launch_count())

@@ -227,6 +227,19 @@ int sydr_trk_state_init(sydr_trk_state* h_state, int prn, double fs, double carr
 int sydr_convert_to_f32(const void* d_in, int iq_dtype, long long n_samples, float* d_out_c64,
                         void* stream);
 
+/* Acquisition -> tracking hand-off on the device (K-HAND), channel_l1ca_borre.py:301-311:
+ * the peaks whose ratio exceeds `threshold` (best first, at most max_channels) become tracking
+ * states ordered by PRN: carrierFrequency = IF - (-range + step * freq_idx), currentSample =
+ * current_sample + required_samples - track_required + code_idx + 1; every other member is
+ * copied from *d_template (loop coefficients, spacings, code NCO at nominal, see
+ * sydr_trk_state_init).  Slots beyond the selected count are marked idle (status 1).
+ * d_n_selected (may be NULL) receives the count.  No host synchronisation. */
+int sydr_acq_handoff(const sydr_acq_peak* d_peaks, int n_prn, double inter_freq, double doppler_range,
+                     double doppler_step, long long required_samples, long long track_required,
+                     long long current_sample, double threshold, const sydr_trk_state* d_template,
+                     long long iq_len, sydr_trk_state* d_states, int max_channels, int* d_n_selected,
+                     void* stream);
+
 /* ------------------------------------------------------------------ nav bits --------- */
 /* Bit synchronisation + navigation-bit accumulation on the device (K-NAV): the scalar state
  * machine ChannelL1CA runs on every tracking result (channel_l1ca_borre.py:398-413 bit-sync

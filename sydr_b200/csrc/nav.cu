@@ -147,3 +147,88 @@ int sydr_nav_bits(const sydr_trk_epoch* d_epochs, int max_epochs, const int* d_n
 }
 
 }  // extern "C"
+
+// ------------------------------------------------------------------------------------------
+// K-HAND: acquisition -> tracking hand-off on the device.
+//
+// Reference semantics: sydr/channel/channel_l1ca_borre.py:301-311 (per channel, host scalars):
+//   doppler = -((-dopplerRange) + dopplerSteps * freq_idx);  carrierFrequency = IF + doppler;
+//   currentSample += acq_requiredSamples - track_requiredSamples + codeOffset + 1.
+// Channel selection is the receiver's (best peak ratios above the threshold, at most
+// max_channels, then ordered by PRN).  Running it here removes the only host round trip between
+// the acquisition and the tracking launch: the tracking kernel is enqueued right behind.
+// ------------------------------------------------------------------------------------------
+namespace sydr {
+
+__global__ void __launch_bounds__(64) acq_handoff_kernel(const sydr_acq_peak* __restrict__ peaks, int n_prn,
+                                                         double inter_freq, double doppler_range, double doppler_step,
+                                                         long long required, long long track_required,
+                                                         long long current_sample, double threshold,
+                                                         const sydr_trk_state* __restrict__ tmpl, long long iq_len,
+                                                         sydr_trk_state* __restrict__ states, int max_channels,
+                                                         int* __restrict__ n_selected) {
+    __shared__ float s_ratio[64];
+    __shared__ int s_prn[64];
+    __shared__ int s_sel[64];
+    const int i = threadIdx.x;
+    sydr_acq_peak pk = {};
+    bool pass = false;
+    if (i < n_prn) {
+        pk = peaks[i];
+        pass = (double)pk.ratio > threshold;
+    }
+    s_ratio[i] = pass ? pk.ratio : -1.f;
+    s_prn[i] = pk.prn;
+    __syncthreads();
+    // rank among the passing peaks: larger ratio first, lower slot first on ties (stable argsort of -ratio)
+    int rank = 0;
+    if (pass)
+        for (int j = 0; j < n_prn; ++j) rank += (s_ratio[j] > pk.ratio) || (s_ratio[j] == pk.ratio && j < i);
+    const bool sel = pass && rank < max_channels;
+    s_sel[i] = sel ? 1 : 0;
+    __syncthreads();
+    int pos = 0, total = 0;
+    for (int j = 0; j < n_prn; ++j) {
+        total += s_sel[j];
+        pos += s_sel[j] && (s_prn[j] < pk.prn || (s_prn[j] == pk.prn && j < i));
+    }
+    if (sel) {
+        sydr_trk_state st = *tmpl;
+        const double doppler = -__dadd_rn(-doppler_range, __dmul_rn(doppler_step, (double)pk.freq_idx));   // L301
+        st.prn = pk.prn;
+        st.carrier_freq = __dadd_rn(inter_freq, doppler);                                                  // L303
+        st.cur = current_sample + required - track_required + (long long)pk.code_idx + 1;                  // L306-311
+        st.iq_base = 0;
+        st.iq_len = iq_len;
+        st.epochs_done = 0;
+        st.status = 0;
+        states[pos] = st;
+    }
+    if (i >= total && i < max_channels) {        // unused slots: idle (the tracking kernel leaves them untouched)
+        sydr_trk_state st = *tmpl;
+        st.prn = 1;
+        st.status = 1;
+        st.iq_len = 0;
+        states[i] = st;
+    }
+    if (i == 0 && n_selected) *n_selected = total;
+}
+
+}  // namespace sydr
+
+extern "C" int sydr_acq_handoff(const sydr_acq_peak* d_peaks, int n_prn, double inter_freq, double doppler_range,
+                                double doppler_step, long long required_samples, long long track_required,
+                                long long current_sample, double threshold, const sydr_trk_state* d_template,
+                                long long iq_len, sydr_trk_state* d_states, int max_channels, int* d_n_selected,
+                                void* stream) {
+    SYDR_REQUIRE(d_peaks && d_template && d_states, SYDR_ERR_ARG, "NULL pointer");
+    SYDR_REQUIRE(n_prn >= 1 && n_prn <= 64 && max_channels >= 1 && max_channels <= 64, SYDR_ERR_ARG,
+                 "n_prn and max_channels must be in [1, 64]");
+    sydr::acq_handoff_kernel<<<1, 64, 0, (cudaStream_t)stream>>>(d_peaks, n_prn, inter_freq, doppler_range, doppler_step,
+                                                                 required_samples, track_required, current_sample,
+                                                                 threshold, d_template, iq_len, d_states, max_channels,
+                                                                 d_n_selected);
+    sydr::count_launch();
+    SYDR_CUDA_CHECK(cudaGetLastError());
+    return SYDR_OK;
+}

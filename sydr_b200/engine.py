@@ -345,7 +345,7 @@ class NavBitEngine:
 
     def launch(self, trk: "TrackingEngine", first_epoch=0, stream=None):
         """Consume records [first_epoch, n) of every channel of `trk` (enqueue after trk.launch)."""
-        assert trk.n_ch == self.n_ch
+        assert trk.n_ch >= self.n_ch                      # the first n_ch slots of the tracking engine
         self.launch_records(trk._out, trk.max_epochs, trk._nep, first_epoch, stream)
 
     def states(self) -> np.ndarray:

@@ -19,6 +19,12 @@ from .engine import (CODE_CHIPS, CODE_FREQ, IQ_PAD_BYTES, AcquisitionEngine, Tra
                      n_complex_samples)
 
 
+def _mark():
+    ev = torch.cuda.Event(enable_timing=True)
+    ev.record()
+    return ev
+
+
 class ColdStartPipeline:
     def __init__(self, fs, nbits, search_prns, n_channels, doppler_range=5000.0, doppler_step=250.0, coh=1,
                  noncoh=10, max_seconds=2.0, inter_freq=0.0, threshold=1.5, channel_cfg=None, device=None,
@@ -38,8 +44,19 @@ class ColdStartPipeline:
         self._tdt = torch.int8 if nbits == 8 else torch.int16
         pad = IQ_PAD_BYTES // (1 if nbits == 8 else 2)
         self._d_iq = torch.zeros(2 * self.max_samples + pad, dtype=self._tdt, device=self.device)
-        self._trk = None
         self._copy_stream = torch.cuda.Stream(device=self.device)
+        self._side_stream = torch.cuda.Stream(device=self.device)
+        # Hand-off on the device (K-HAND): a template state with the loop coefficients, the tracking
+        # engine for n_channels slots (unused ones idle) and a pinned landing zone for the peak table,
+        # so that acquisition, hand-off and tracking are enqueued back to back with no host round trip.
+        tmpl = make_trk_states(self.fs, [dict(prn=1, carrier_freq=0.0, start_sample=0)], channel_cfg)
+        self._tmpl = torch.from_numpy(tmpl.view(np.uint8).reshape(-1).copy()).to(self.device)
+        idle = np.repeat(tmpl, self.n_channels)
+        idle["status"] = 1
+        self._trk = TrackingEngine(self.fs, idle, self.max_epochs, device=self.device, **self.trk_cfg)
+        self._n_sel = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self._peaks_host = torch.empty(len(self.acq.prns) * 24, dtype=torch.uint8, pin_memory=True)
+        self._track_required = int(math.ceil(CODE_CHIPS / (CODE_FREQ / self.fs)))
 
     def close(self):
         self.acq.close()
@@ -63,34 +80,59 @@ class ColdStartPipeline:
         sel = [i for i in order if peaks["ratio"][i] > self.threshold][:self.n_channels]
         return sorted(sel, key=lambda i: int(peaks["prn"][i]))
 
-    def _start_tracking(self, peaks: np.ndarray, n_samples: int):
-        """Scalar hand-off (channel_l1ca_borre.py:301-316) and fresh channel states on the device."""
-        sel = self.select_channels(peaks)
+    def _handoff(self, n_samples: int, stream=None):
+        """Enqueue K-HAND: peak table -> channel states on the device (channel_l1ca_borre.py:301-311)."""
+        a = self.acq
+        L.check(L.load().sydr_acq_handoff(a.peaks_device().data_ptr(), len(a.prns), a.inter_freq, a.doppler_range,
+                                          a.doppler_step, a.required_samples, self._track_required, 0,
+                                          self.threshold, self._tmpl.data_ptr(), int(n_samples),
+                                          self._trk._states.data_ptr(), self.n_channels, self._n_sel.data_ptr(),
+                                          (stream or torch.cuda.current_stream()).cuda_stream), "sydr_acq_handoff")
+
+    def _peaks_to_host_async(self):
+        """Copy the peak table to pinned memory on a side stream, behind the acquisition only."""
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream())
+        self._side_stream.wait_event(ev)
+        with torch.cuda.stream(self._side_stream):
+            self._peaks_host.copy_(self.acq.peaks_device(), non_blocking=True)
+            done = torch.cuda.Event()
+            done.record(self._side_stream)
+        return done
+
+    def _channels_of(self, peaks: np.ndarray, n_samples: int):
+        """The channel list the device hand-off produced, restated on the host for the caller."""
         chans = []
-        for i in sel:
+        for i in self.select_channels(peaks):
             carrier, _, cur = self.acq.handoff(peaks[i])
             chans.append(dict(prn=int(peaks["prn"][i]), carrier_freq=carrier, start_sample=cur, iq_len=n_samples))
-        states = make_trk_states(self.fs, chans, self.channel_cfg)
-        if self._trk is None or self._trk.n_ch != len(chans):
-            self._trk = TrackingEngine(self.fs, states, self.max_epochs, device=self.device, **self.trk_cfg)
-        else:
-            self._trk.reset(states)
         return chans
 
-    def process_device(self, d_iq: torch.Tensor) -> dict:
-        """Acquisition + hand-off + tracking on IQ already resident in HBM."""
+    def process_device(self, d_iq: torch.Tensor, marks: list | None = None) -> dict:
+        """Acquisition + hand-off + tracking on IQ already resident in HBM: three launches back to
+        back, the peak table travels to the host while the channels are being tracked.  `marks`
+        (optional) receives four timing events: before / after the acquisition, before / after tracking."""
         n = n_complex_samples(d_iq)
+        mark = (lambda: marks.append(_mark())) if marks is not None else (lambda: None)
+        mark()
         self.acq.launch(d_iq)
-        peaks = self.acq.fetch()["peaks"]                       # 24 B per PRN, D2H
-        chans = self._start_tracking(peaks, n)
+        mark()
+        got = self._peaks_to_host_async()
+        self._handoff(n)
+        mark()
         self._trk.launch(d_iq)
+        mark()
+        got.synchronize()
+        peaks = self._peaks_host.numpy().view(L.ACQ_PEAK_DTYPE).copy()
+        chans = self._channels_of(peaks, n)
+        self._n_active = len(chans)
         return dict(peaks=peaks, channels=chans)
 
     def collect(self) -> list:
         """D2H of the per-epoch tracking records of the last process_*()."""
-        return self._trk.fetch()
+        return self._trk.fetch()[:self._n_active]
 
-    def process_host(self, host_iq: torch.Tensor, pieces: int = 8) -> dict:
+    def process_host(self, host_iq: torch.Tensor, pieces: int = 4) -> dict:
         """End to end: pinned host IQ in, acquisition table + per-epoch tracking records out.
         The upload is cut into `pieces` segments on a copy stream; acquisition starts as soon as
         the dwell has landed and tracking follows the upload piece by piece (state carried on
@@ -118,11 +160,15 @@ class ColdStartPipeline:
                 lo = hi
         comp.wait_event(events[0])
         self.acq.launch(d[:2 * first])
-        peaks = self.acq.fetch()["peaks"]
-        chans = self._start_tracking(peaks, n)
+        got = self._peaks_to_host_async()
+        self._handoff(n)
         for hi, ev in zip(bounds, events):
             comp.wait_event(ev)
             self._trk.launch(d, iq_len=hi, append=True)
+        got.synchronize()
+        peaks = self._peaks_host.numpy().view(L.ACQ_PEAK_DTYPE).copy()
+        chans = self._channels_of(peaks, n)
+        self._n_active = len(chans)
         out = dict(peaks=peaks, channels=chans)
         out["epochs"] = self.collect()
         return out
