@@ -312,7 +312,10 @@ def workload_config(args, world):
                         "per step): 32-PRN PCPS acquisition (+-5 kHz/250 Hz, 1 ms x 10) + 12-channel closed-loop E/P/L tracking",
             "fs_hz": FS, "iq": "int16", "chunk_seconds": args.chunk_seconds, "search_prns": 32, "channels": N_CHANNELS,
             "recordings": world, "parallelism": f"recording-per-gpu x{world}",
-            "l2": f"input chunk {args.chunk_seconds * FS * 4 / 1e6:.0f} MB per step exceeds the 126 MB L2"}
+            "l2": f"input chunk {args.chunk_seconds * FS * 4 / 1e6:.0f} MB per step exceeds the 126 MB L2",
+            "e2e_call": "ColdStartPipeline.process_host(pinned int16 IQ): H2D in 4 pieces on a copy stream, acquisition, "
+                        "device hand-off, tracking behind the upload, D2H of peak table and all epoch records into a ring "
+                        "of pinned result buffers (returned as views)"}
 
 
 def main():

@@ -224,8 +224,13 @@ class TrackingEngine:
         self._states = torch.from_numpy(st.view(np.uint8).reshape(-1).copy()).to(self.device)
         self._out = torch.empty(self.n_ch * self.max_epochs * 128, dtype=torch.uint8, device=self.device)
         self._nep = torch.zeros(self.n_ch, dtype=torch.int32, device=self.device)
-        # pinned staging for the results: one asynchronous D2H per fetch, no pageable bounce
-        self._out_host = torch.empty(self.n_ch * self.max_epochs * 128, dtype=torch.uint8, pin_memory=True)
+        # pinned staging for the results: one asynchronous D2H per fetch, no pageable bounce.  A ring of
+        # buffers, so that fetch(copy=False) can hand out views that survive the next fetches.
+        self.RING = 4
+        self._out_ring = [torch.empty(self.n_ch * self.max_epochs * 128, dtype=torch.uint8, pin_memory=True)
+                          for _ in range(self.RING)]
+        self._ring_i = 0
+        self._out_host = self._out_ring[0]
         self._nep_host = torch.zeros(self.n_ch, dtype=torch.int32, pin_memory=True)
 
     def set_iq_len(self, iq_len):
@@ -261,13 +266,20 @@ class TrackingEngine:
     def states(self) -> np.ndarray:
         return self._states.cpu().numpy().view(L.TRK_STATE_DTYPE).copy()
 
-    def fetch(self):
+    def fetch(self, copy: bool = True):
+        """Per-channel record arrays of everything tracked since the last reset.  copy=False returns
+        views of pinned staging memory (no host copy, no page faults: ~1 ms saved per 3 MB); they stay
+        valid until RING - 1 further fetches of this engine."""
+        self._ring_i = (self._ring_i + 1) % self.RING
+        self._out_host = self._out_ring[self._ring_i]
         self._nep_host.copy_(self._nep, non_blocking=True)
         self._out_host.copy_(self._out, non_blocking=True)
         torch.cuda.current_stream().synchronize()
-        nep = self._nep_host.numpy()
+        nep = self._nep_host.numpy().copy()
         out = self._out_host.numpy().view(L.TRK_EPOCH_DTYPE).reshape(self.n_ch, self.max_epochs)
-        return [out[c, :nep[c]].copy() for c in range(self.n_ch)]
+        if copy:
+            return [out[c, :nep[c]].copy() for c in range(self.n_ch)]
+        return [out[c, :nep[c]] for c in range(self.n_ch)]
 
     def run(self, iq_dev: torch.Tensor, stream=None):
         self.launch(iq_dev, stream=stream)
