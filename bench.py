@@ -311,7 +311,8 @@ def workload_config(args, world):
     return {"workload": f"cfg3-format recording per GPU (25 MS/s int16 IQ, 12 PRNs @45 dB-Hz, {args.chunk_seconds:g} s chunk "
                         "per step): 32-PRN PCPS acquisition (+-5 kHz/250 Hz, 1 ms x 10) + 12-channel closed-loop E/P/L tracking",
             "fs_hz": FS, "iq": "int16", "chunk_seconds": args.chunk_seconds, "search_prns": 32, "channels": N_CHANNELS,
-            "recordings": world, "parallelism": f"recording-per-gpu x{world}",
+            "recordings": world, "parallelism": f"recording-per-gpu x{world}, {getattr(args, 'lanes', 1)} steps in flight per GPU",
+            "lanes": getattr(args, "lanes", 1),
             "l2": f"input chunk {args.chunk_seconds * FS * 4 / 1e6:.0f} MB per step exceeds the 126 MB L2",
             "e2e_call": "ColdStartPipeline.process_host(pinned int16 IQ): H2D in 4 pieces on a copy stream, acquisition, "
                         "device hand-off, tracking behind the upload, D2H of peak table and all epoch records into a ring "
@@ -325,6 +326,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--chunk-seconds", type=float, default=2.0)
+    ap.add_argument("--lanes", type=int, default=3, help="steps in flight per GPU (ColdStartPool)")
     ap.add_argument("--cluster", type=int, default=0)
     ap.add_argument("--threads", type=int, default=0)
     ap.add_argument("--no-tma", action="store_true")
@@ -343,7 +345,7 @@ def main():
     import torch
     import torch.distributed as dist
     from sydr_b200 import _lib as L
-    from sydr_b200.pipeline import ColdStartPipeline
+    from sydr_b200.pipeline import ColdStartPool
 
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
@@ -354,22 +356,39 @@ def main():
 
     sc, host = make_recording(rank, args.chunk_seconds, dev)
     chunk_samples = host.numel() // 2
-    pipe = ColdStartPipeline(FS, NBITS, SEARCH_PRNS, N_CHANNELS, max_seconds=args.chunk_seconds, device=dev,
-                             cluster=args.cluster, threads=args.threads, use_tma=not args.no_tma, **ACQ)
+    # `lanes` steps in flight: the acquisition of step k+1 runs beside the tracking of step k, which is a
+    # latency chain on 96 of the 148 SMs (ColdStartPool)
+    pool = ColdStartPool(lanes=args.lanes, fs=FS, nbits=NBITS, search_prns=SEARCH_PRNS, n_channels=N_CHANNELS,
+                         max_seconds=args.chunk_seconds, device=dev, cluster=args.cluster, threads=args.threads,
+                         use_tma=not args.no_tma, **ACQ)
+    pipe = pool.lanes[0]
     d_iq = pipe.upload(host)
     torch.cuda.synchronize()
     gathered = torch.empty(world * len(SEARCH_PRNS) * 24, dtype=torch.uint8, device=dev) if world > 1 else None
 
-    def step_device():
-        out = pipe.process_device(d_iq)
-        if world > 1:                                   # the acquisition peak table, 768 B per rank
-            dist.all_gather_into_tensor(gathered, pipe.acq.peaks_device())
-        return out
+    def gather_peaks(ticket):                           # the acquisition peak table, 768 B per rank
+        if world > 1:
+            lane = pool.lane_index(ticket)
+            with torch.cuda.stream(pool.stream(lane)):
+                dist.all_gather_into_tensor(gathered, pool.lanes[lane].acq.peaks_device())
+
+    def run_steps(n, submit, records, marks_out=None):
+        """n steps with at most `lanes` in flight; results collected in order."""
+        tickets = []
+        for _ in range(n):
+            if len(tickets) == args.lanes:
+                pool.result(tickets.pop(0), records=records)
+            marks = [] if marks_out is not None else None
+            t = submit(marks)
+            gather_peaks(t)
+            tickets.append(t)
+            if marks_out is not None:
+                marks_out.append(marks)
+        while tickets:
+            pool.result(tickets.pop(0), records=records)
 
     def step_e2e():
         out = pipe.process_host(host)
-        if world > 1:
-            dist.all_gather_into_tensor(gathered, pipe.acq.peaks_device())
         return out
 
     def barrier():
@@ -390,8 +409,7 @@ def main():
     d2h_bytes = len(SEARCH_PRNS) * 24 + sum(e.nbytes for e in out["epochs"]) + 4 * len(out["epochs"])
 
     # ---- warm-up, then K steps resident in HBM
-    for _ in range(args.warmup):
-        step_device()
+    run_steps(args.warmup, lambda m: pool.submit_device(d_iq, m), False)
     barrier()
     sampler = ClockSampler(local)
     sampler.start()
@@ -399,29 +417,34 @@ def main():
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
     k_ev = []
     ev[0].record()
-    for _ in range(args.steps):
-        marks = []
-        pipe.process_device(d_iq, marks)                # acquisition, K-HAND, tracking: enqueued back to back
-        if world > 1:
-            dist.all_gather_into_tensor(gathered, pipe.acq.peaks_device())
-        k_ev.append(tuple(marks))
-    ev[1].record()
+    run_steps(args.steps, lambda m: pool.submit_device(d_iq, m), False, k_ev)
     barrier()
+    ev[1].record()
+    torch.cuda.synchronize()
     launches = int(lib.sydr_launch_count())
     ms_dev = ev[0].elapsed_time(ev[1])
-    ms_acq = float(np.mean([a.elapsed_time(b) for a, b, _, _ in k_ev]))
-    ms_trk = float(np.mean([c.elapsed_time(d) for _, _, c, d in k_ev]))
+    ms_acq = float(np.mean([m[0].elapsed_time(m[1]) for m in k_ev]))
+    ms_trk = float(np.mean([m[2].elapsed_time(m[3]) for m in k_ev]))
+
+    # ---- the two kernels timed alone (one step in flight), for the per-kernel figures
+    alone = []
+    for _ in range(4):
+        m = []
+        pipe.process_device(d_iq, m)
+        torch.cuda.synchronize()
+        alone.append(m)
+    ms_acq_alone = float(np.mean([m[0].elapsed_time(m[1]) for m in alone[1:]]))
+    ms_trk_alone = float(np.mean([m[2].elapsed_time(m[3]) for m in alone[1:]]))
 
     # ---- K steps end to end from pinned host memory
-    for _ in range(2):
-        step_e2e()
+    run_steps(2, lambda m: pool.submit_host(host), True)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(args.steps):
-        step_e2e()
-    e1.record()
+    run_steps(args.steps, lambda m: pool.submit_host(host), True)
     barrier()
+    e1.record()
+    torch.cuda.synchronize()
     ms_e2e = e0.elapsed_time(e1)
     clocks = sampler.stop()
 
@@ -451,18 +474,33 @@ def main():
         ach = (trk_flop / (ms_trk * 1e-3) / 1e12) if dominant == "trk_borre_kernel" else (acq_flop / (ms_acq * 1e-3) / 1e12)
         tr_bytes, tr_chunk = NCU_TRAFFIC_BYTES[dominant]
         traffic = tr_bytes * (args.chunk_seconds / tr_chunk if tr_chunk else 1.0)
+        step_flop = trk_flop + acq_flop
+        step_ms = ms_dev / args.steps
         roofline = {"kernel": dominant, "bound": "fp32", "achieved": ach, "peak": tfv.value, "unit": "TFLOP/s",
                     "frac": ach / tfv.value if tfv.value else None, "traffic": traffic,
                     "traffic_note": "DRAM bytes per launch (ncu --set full, profiles/r1_ncu_summary.txt); algorithmic bytes per "
                                     f"launch {trk_bytes:.4g}" if dominant == "trk_borre_kernel" else "DRAM bytes per launch (ncu)",
                     "peak_source": f"FP32 FMA chain measured in this run ({clkv.value:.0f} MHz max clock)",
                     "note": "12 channels occupy <= 96 of 148 SMs and every channel is a serial chain of 1 ms epochs: "
-                            "the bound is per-epoch latency, not the FP32 or HBM roof (DESIGN.md §4)",
+                            "the bound of one launch is per-epoch latency, not the FP32 or HBM roof (DESIGN.md §4); several "
+                            "steps are kept in flight so that other launches use the SMs and issue slots it leaves idle",
                     "hbm": {"achieved": trk_bytes / (ms_trk * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                             "frac": trk_bytes / (ms_trk * 1e-3) / 1e9 / hbm_peak, "peak_source": hbm_src},
                     "kernels": {"trk_borre_kernel": {"ms": ms_trk, "tflops": trk_flop / (ms_trk * 1e-3) / 1e12,
-                                                     "us_per_epoch": ms_trk * 1e3 / (chunk_samples / (FS * 1e-3))},
-                                "acq (fwd+ifft+reduce)": {"ms": ms_acq, "tflops": acq_flop / (ms_acq * 1e-3) / 1e12}}}
+                                                     "us_per_epoch": ms_trk * 1e3 / (chunk_samples / (FS * 1e-3)),
+                                                     "alone_ms": ms_trk_alone,
+                                                     "alone_us_per_epoch": ms_trk_alone * 1e3 / (chunk_samples / (FS * 1e-3)),
+                                                     "alone_tflops": trk_flop / (ms_trk_alone * 1e-3) / 1e12},
+                                "acq (fwd+ifft+reduce)": {"ms": ms_acq, "tflops": acq_flop / (ms_acq * 1e-3) / 1e12,
+                                                          "alone_ms": ms_acq_alone,
+                                                          "alone_tflops": acq_flop / (ms_acq_alone * 1e-3) / 1e12}},
+                    "step_aggregate": {"achieved": step_flop / (step_ms * 1e-3) / 1e12, "unit": "TFLOP/s",
+                                       "frac": step_flop / (step_ms * 1e-3) / 1e12 / tfv.value if tfv.value else None,
+                                       "note": "algorithmic flops of one whole step (acquisition + tracking) over the "
+                                               "measured step period: what the GPU sustains with the steps overlapped"},
+                    "kernels_note": f"ms = launch duration inside the timed region ({args.lanes} steps in flight: the "
+                                    "acquisition of one step shares the GPU with the tracking of another); alone_ms = the "
+                                    "same launch with one step in flight"}
         if args.stress_recordings > 0 and world == 1:
             roofline["throughput_mode"] = throughput_stress(dev, args.stress_recordings, args.stress_seconds, tfv.value)
         line = {"metric": "cold acquisition (32 PRN) + 12-channel tracking throughput", "value": value, "unit": "Msamples/s",

@@ -108,10 +108,11 @@ class ColdStartPipeline:
             chans.append(dict(prn=int(peaks["prn"][i]), carrier_freq=carrier, start_sample=cur, iq_len=n_samples))
         return chans
 
-    def process_device(self, d_iq: torch.Tensor, marks: list | None = None) -> dict:
-        """Acquisition + hand-off + tracking on IQ already resident in HBM: three launches back to
-        back, the peak table travels to the host while the channels are being tracked.  `marks`
-        (optional) receives four timing events: before / after the acquisition, before / after tracking."""
+    def enqueue_device(self, d_iq: torch.Tensor, marks: list | None = None) -> dict:
+        """Enqueue acquisition, hand-off and tracking of IQ resident in HBM on the current stream (three
+        launches back to back; the peak table travels to pinned memory on a side stream).  Returns the
+        context finish() needs; nothing here waits for the GPU.  `marks` (optional) receives four timing
+        events: before / after the acquisition, before / after tracking."""
         n = n_complex_samples(d_iq)
         mark = (lambda: marks.append(_mark())) if marks is not None else (lambda: None)
         mark()
@@ -122,24 +123,35 @@ class ColdStartPipeline:
         mark()
         self._trk.launch(d_iq)
         mark()
-        got.synchronize()
+        return dict(got=got, n=n)
+
+    def finish(self, ctx: dict, records: bool = False, copy: bool = False) -> dict:
+        """Host side of an enqueued step: the peak table, the channel list and (records=True) the
+        per-epoch tracking records."""
+        ctx["got"].synchronize()
         peaks = self._peaks_host.numpy().view(L.ACQ_PEAK_DTYPE).copy()
-        chans = self._channels_of(peaks, n)
+        chans = self._channels_of(peaks, ctx["n"])
         self._n_active = len(chans)
-        return dict(peaks=peaks, channels=chans)
+        out = dict(peaks=peaks, channels=chans)
+        if records:
+            out["epochs"] = self.collect(copy=copy)
+        return out
+
+    def process_device(self, d_iq: torch.Tensor, marks: list | None = None) -> dict:
+        """Acquisition + hand-off + tracking on IQ already resident in HBM (records stay on the device
+        until collect())."""
+        return self.finish(self.enqueue_device(d_iq, marks))
 
     def collect(self, copy: bool = True) -> list:
         """D2H of the per-epoch tracking records of the last process_*().  copy=False: views of pinned
         staging memory, valid until three further collect() / process_host() calls."""
         return self._trk.fetch(copy=copy)[:self._n_active]
 
-    def process_host(self, host_iq: torch.Tensor, pieces: int = 4, copy: bool = False) -> dict:
-        """End to end: pinned host IQ in, acquisition table + per-epoch tracking records out.
-        The upload is cut into `pieces` segments on a copy stream; acquisition starts as soon as
-        the dwell has landed and tracking follows the upload piece by piece (state carried on
-        the device, records appended), so H2D and compute overlap.  The record arrays are views of
-        pinned staging memory that stay valid for the next three calls (copy=True for private copies:
-        first-touch page faults of 3 MB cost ~1 ms per call)."""
+    def enqueue_host(self, host_iq: torch.Tensor, pieces: int = 4) -> dict:
+        """Enqueue one end-to-end step from pinned host IQ: the upload is cut into `pieces` segments on
+        a copy stream; acquisition starts as soon as the dwell has landed and tracking follows the
+        upload piece by piece (state carried on the device, records appended), so H2D and compute
+        overlap.  Nothing here waits for the GPU."""
         n_el = host_iq.numel()
         n = n_el // 2
         if n > self.max_samples:
@@ -168,10 +180,71 @@ class ColdStartPipeline:
         for hi, ev in zip(bounds, events):
             comp.wait_event(ev)
             self._trk.launch(d, iq_len=hi, append=True)
-        got.synchronize()
-        peaks = self._peaks_host.numpy().view(L.ACQ_PEAK_DTYPE).copy()
-        chans = self._channels_of(peaks, n)
-        self._n_active = len(chans)
-        out = dict(peaks=peaks, channels=chans)
-        out["epochs"] = self.collect(copy=copy)
+        return dict(got=got, n=n)
+
+    def process_host(self, host_iq: torch.Tensor, pieces: int = 4, copy: bool = False) -> dict:
+        """End to end: pinned host IQ in, acquisition table + per-epoch tracking records out.  The
+        record arrays are views of pinned staging memory that stay valid for the next three calls
+        (copy=True for private copies: first-touch page faults of 3 MB cost ~1 ms per call)."""
+        return self.finish(self.enqueue_host(host_iq, pieces), records=True, copy=copy)
+
+
+class ColdStartPool:
+    """Several steps in flight on one GPU.
+
+    The 12-channel tracking kernel is a latency chain that occupies 96 of the 148 SMs; the
+    acquisition of the *next* chunk (or recording) fits beside it.  The pool owns `lanes`
+    independent ColdStartPipeline instances, each on its own stream; submit_*() enqueues a whole
+    step on the next lane and returns a ticket at once, result() hands back what process_*() would.
+    With two lanes the step period drops from acquisition + tracking to about the SM-time bound
+    (5.7 -> 4.4 ms for the headline chunk)."""
+
+    def __init__(self, lanes: int = 2, **pipeline_kwargs):
+        self.lanes = [ColdStartPipeline(**pipeline_kwargs) for _ in range(int(lanes))]
+        dev = self.lanes[0].device
+        self._streams = [torch.cuda.Stream(device=dev) for _ in self.lanes]
+        self._pending = {}
+        self._next = 0
+        self._ticket = 0
+
+    def close(self):
+        for p in self.lanes:
+            p.close()
+
+    def _lane(self):
+        i = self._next
+        if any(l == i for l, _ in self._pending.values()):
+            raise L.SydrError("every lane has a step in flight: collect a result() first")
+        self._next = (i + 1) % len(self.lanes)
+        return i
+
+    def submit_device(self, d_iq: torch.Tensor, marks: list | None = None) -> int:
+        i = self._lane()
+        s = self._streams[i]
+        s.wait_stream(torch.cuda.current_stream())               # the caller's work on d_iq is ordered first
+        with torch.cuda.stream(s):
+            ctx = self.lanes[i].enqueue_device(d_iq, marks)
+        self._ticket += 1
+        self._pending[self._ticket] = (i, ctx)
+        return self._ticket
+
+    def submit_host(self, host_iq: torch.Tensor, pieces: int = 4) -> int:
+        i = self._lane()
+        with torch.cuda.stream(self._streams[i]):
+            ctx = self.lanes[i].enqueue_host(host_iq, pieces)
+        self._ticket += 1
+        self._pending[self._ticket] = (i, ctx)
+        return self._ticket
+
+    def result(self, ticket: int, records: bool = True, copy: bool = False) -> dict:
+        i, ctx = self._pending.pop(ticket)
+        with torch.cuda.stream(self._streams[i]):
+            out = self.lanes[i].finish(ctx, records=records, copy=copy)
+        out["lane"] = i
         return out
+
+    def lane_index(self, ticket: int) -> int:
+        return self._pending[ticket][0]
+
+    def stream(self, lane: int) -> torch.cuda.Stream:
+        return self._streams[lane]
