@@ -369,7 +369,7 @@ def main():
     def gather_peaks(ticket):                           # the acquisition peak table, 768 B per rank
         if world > 1:
             lane = pool.lane_index(ticket)
-            with torch.cuda.stream(pool.stream(lane)):
+            with torch.cuda.stream(pool.peak_stream(lane)):          # behind the acquisition, beside the tracking
                 dist.all_gather_into_tensor(gathered, pool.lanes[lane].acq.peaks_device())
 
     def run_steps(n, submit, records, marks_out=None):

@@ -248,3 +248,8 @@ class ColdStartPool:
 
     def stream(self, lane: int) -> torch.cuda.Stream:
         return self._streams[lane]
+
+    def peak_stream(self, lane: int) -> torch.cuda.Stream:
+        """The lane's side stream: ordered behind its acquisition (peak table complete), not behind its
+        tracking.  Where a multi-GPU caller enqueues the all-gather of the 768-byte peak table."""
+        return self.lanes[lane]._side_stream
