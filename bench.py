@@ -470,16 +470,29 @@ def main():
         trk_bytes = 4.0 * chunk_samples + 128.0 * n_ch * (chunk_samples / (FS * 1e-3))
         n_code = int(FS * 1e-3)
         acq_flop = len(SEARCH_PRNS) * 41 * ACQ["coh"] * ACQ["noncoh"] * f_acq(n_code)
-        dominant = "trk_borre_kernel" if ms_trk >= ms_acq else "acq_ifft_kernel"
-        ach = (trk_flop / (ms_trk * 1e-3) / 1e12) if dominant == "trk_borre_kernel" else (acq_flop / (ms_acq * 1e-3) / 1e12)
-        tr_bytes, tr_chunk = NCU_TRAFFIC_BYTES[dominant]
-        traffic = tr_bytes * (args.chunk_seconds / tr_chunk if tr_chunk else 1.0)
+        # With several steps in flight the launches of different steps overlap on the GPU, so a launch's
+        # duration on its own stream is no longer the time the GPU spends on it.  The physically meaningful
+        # figure over the timed region is the aggregate: algorithmic flops of the K steps / the time they took.
+        # The per-kernel figures (inside the region and alone) are listed under "kernels".
         step_flop = trk_flop + acq_flop
-        step_ms = ms_dev / args.steps
-        roofline = {"kernel": dominant, "bound": "fp32", "achieved": ach, "peak": tfv.value, "unit": "TFLOP/s",
+        step_ms = ms_dev / args.steps                              # step period of one GPU (roofline is per GPU)
+        ach = step_flop / (step_ms * 1e-3) / 1e12
+        dominant = "trk_borre_kernel" if ms_trk_alone >= ms_acq_alone else "acq_ifft_kernel"
+        traffic = NCU_TRAFFIC_BYTES["trk_borre_kernel"][0] * (args.chunk_seconds / NCU_TRAFFIC_BYTES["trk_borre_kernel"][1]) \
+            + NCU_TRAFFIC_BYTES["acq_ifft_kernel"][0]
+        ach_dom_alone = (trk_flop / (ms_trk_alone * 1e-3) / 1e12) if dominant == "trk_borre_kernel" else (acq_flop / (ms_acq_alone * 1e-3) / 1e12)
+        ach_dom_in = (trk_flop / (ms_trk * 1e-3) / 1e12) if dominant == "trk_borre_kernel" else (acq_flop / (ms_acq * 1e-3) / 1e12)
+        roofline = {"kernel": f"acq_fwd_kernel + acq_ifft_kernel + trk_borre_kernel of {args.lanes} overlapped steps (aggregate over the timed region)",
+                    "bound": "fp32", "achieved": ach, "peak": tfv.value, "unit": "TFLOP/s",
                     "frac": ach / tfv.value if tfv.value else None, "traffic": traffic,
-                    "traffic_note": "DRAM bytes per launch (ncu --set full, profiles/r1_ncu_summary.txt); algorithmic bytes per "
-                                    f"launch {trk_bytes:.4g}" if dominant == "trk_borre_kernel" else "DRAM bytes per launch (ncu)",
+                    "traffic_note": "DRAM bytes per step: trk_borre_kernel + acq_ifft_kernel launches (ncu --set full, "
+                                    f"profiles/r1_ncu_summary.txt); algorithmic bytes per step {trk_bytes:.4g}",
+                    "dominant_kernel": {"name": dominant, "achieved_alone": ach_dom_alone,
+                                        "frac_alone": ach_dom_alone / tfv.value if tfv.value else None,
+                                        "achieved_in_region": ach_dom_in,
+                                        "frac_in_region": ach_dom_in / tfv.value if tfv.value else None,
+                                        "definition": "algorithmic flops per launch / average launch duration (CUDA events "
+                                                      "on the launching stream); alone = one step in flight"},
                     "peak_source": f"FP32 FMA chain measured in this run ({clkv.value:.0f} MHz max clock)",
                     "note": "12 channels occupy <= 96 of 148 SMs and every channel is a serial chain of 1 ms epochs: "
                             "the bound of one launch is per-epoch latency, not the FP32 or HBM roof (DESIGN.md §4); several "
@@ -494,10 +507,6 @@ def main():
                                 "acq (fwd+ifft+reduce)": {"ms": ms_acq, "tflops": acq_flop / (ms_acq * 1e-3) / 1e12,
                                                           "alone_ms": ms_acq_alone,
                                                           "alone_tflops": acq_flop / (ms_acq_alone * 1e-3) / 1e12}},
-                    "step_aggregate": {"achieved": step_flop / (step_ms * 1e-3) / 1e12, "unit": "TFLOP/s",
-                                       "frac": step_flop / (step_ms * 1e-3) / 1e12 / tfv.value if tfv.value else None,
-                                       "note": "algorithmic flops of one whole step (acquisition + tracking) over the "
-                                               "measured step period: what the GPU sustains with the steps overlapped"},
                     "kernels_note": f"ms = launch duration inside the timed region ({args.lanes} steps in flight: the "
                                     "acquisition of one step shares the GPU with the tracking of another); alone_ms = the "
                                     "same launch with one step in flight"}

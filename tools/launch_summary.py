@@ -9,7 +9,7 @@ import sys
 from collections import OrderedDict
 
 OURS = ("trk_borre_kernel", "epl_batch_kernel", "acq_", "ca_code_kernel", "code_spectrum", "peak_rows", "convert_",
-        "fp32_peak", "fp64_peak", "kaplan", "bitsync", "sydr")
+        "fp32_peak", "fp64_peak", "kaplan", "bitsync", "nav_bits", "acq_handoff", "sydr")
 
 
 def short(name):
