@@ -1533,8 +1533,12 @@ int sydr_trk_run(const void* d_iq, int iq_dtype, long long iq_alloc_samples, dou
         cluster <<= 1;                                     // (the chunk size chosen above is kept)
     const int Q = (int)((n_max + spv + (long long)C * cluster - 1) / ((long long)C * cluster));
     if (threads <= 0) {
-        const int rounds = (Q + kTrkMaxThreads - 1) / kTrkMaxThreads;
-        threads = (((Q + rounds - 1) / rounds) + 31) / 32 * 32;
+        // Two thirds of a thread per chunk / segment: the epoch is a latency chain, not a throughput
+        // problem (2.00 us with 192 threads, 2.01 with 288 at 25 MS/s), and the smaller CTA leaves
+        // registers and issue slots to whatever shares the SM (other steps in flight, ColdStartPool).
+        const int want = (2 * Q + 2) / 3;
+        const int rounds = (want + kTrkMaxThreads - 1) / kTrkMaxThreads;
+        threads = (((want + rounds - 1) / rounds) + 31) / 32 * 32;
         if (threads < 64) threads = 64;                    // warps 0 and 1 close the two loops
     }
     SYDR_REQUIRE(threads % 32 == 0 && threads >= 64 && threads <= kTrkMaxThreads, SYDR_ERR_ARG, "threads must be a multiple of 32 in [64, %d] (got %d)", kTrkMaxThreads, threads);
