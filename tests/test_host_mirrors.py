@@ -91,3 +91,33 @@ def test_min_tap_gap():
     assert min_tap_gap(np.array([[-0.5, 0.0, 0.5]])) == 0.5
     assert abs(min_tap_gap(np.array([[-0.25, 0.0, 0.25]])) - 0.25) < 1e-12
     assert abs(min_tap_gap(np.array([[-0.5, 0.0, 0.5], [-0.1, 0.0, 0.1]])) - 0.1) < 1e-12
+
+
+def test_file_chunk_reader_delivers_the_file_bytes(tmp_path):
+    """Ingest host logic (no GPU): consecutive chunks into rotating buffers, ragged last chunk,
+    skip / max_samples windows, parallel preadv pieces that tile each chunk exactly."""
+    from sydr_b200.ingest import FileChunkReader
+    rng = np.random.default_rng(3)
+    for dt in (np.int8, np.int16):
+        raw = rng.integers(-100, 100, 2 * 10007, dtype=dt)              # 10007 complex samples
+        path = str(tmp_path / f"iq_{np.dtype(dt).itemsize}.bin")
+        raw.tofile(path)
+        for chunk, skip, mx, thr in ((1000, 0, None, 4), (4096, 123, 7001, 3), (20000, 0, None, 1), (999, 10006, None, 2)):
+            rd = FileChunkReader(path, dt, chunk, skip_samples=skip, max_samples=mx, n_buffers=2, threads=thr)
+            got = []
+            for k, slot, buf, n in rd:
+                assert k == len(got) and buf.numel() == 2 * n and n <= chunk
+                got.append(buf.numpy().copy())
+                rd.release(slot)
+            rd.close()
+            total = min(10007 - skip, mx) if mx is not None else 10007 - skip
+            want = raw[2 * skip:2 * (skip + total)]
+            assert rd.n_chunks == -(-total // chunk) == len(got)
+            assert np.array_equal(np.concatenate(got), want)
+
+
+def test_new_struct_layouts():
+    import ctypes as C
+    from sydr_b200 import _lib as L
+    assert L.NAV_STATE_DTYPE.itemsize == 48 and L.NAV_STATE_DTYPE.fields["nav_count"][1] == 40
+    assert C.sizeof(L.TrkConfig) == 48 and L.TrkConfig.iq_base.offset == 32 and L.TrkConfig.use_iq_base.offset == 40
