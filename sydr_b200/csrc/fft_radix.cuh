@@ -1,4 +1,4 @@
-// In-register forward DFT butterflies (radix 2, 3, 4, 5 and Cooley-Tukey composites 8, 10, 16,
+// In-register forward DFT butterflies (radix 2, 3, 4, 5, prime-factor 10 and Cooley-Tukey composites 8, 16,
 // 20, 25) for the shared-memory mixed-radix FFT of the acquisition kernels.
 //
 // Only *forward* butterflies exist: the inverse transform is run as a forward transform on
@@ -102,7 +102,27 @@ struct DftCT {
     }
 };
 template <> struct Dft<8>  { __device__ static __forceinline__ void run(float2* u) { DftCT<2, 4>::run(u); } };
-template <> struct Dft<10> { __device__ static __forceinline__ void run(float2* u) { DftCT<2, 5>::run(u); } };
+// Radix 10 by the prime-factor (Good-Thomas) map, 2 and 5 being coprime: n = (5 n1 + 2 n2) mod 10,
+// k = (5 k1 + 6 k2) mod 10 turns the length-10 DFT into a 2 x 5 two-dimensional DFT with no twiddle
+// factors in between (the Cooley-Tukey split spends four complex multiplications on them).
+template <> struct Dft<10> {
+    __device__ static __forceinline__ void run(float2* u) {
+        float2 a[5], b[5];
+#pragma unroll
+        for (int n2 = 0; n2 < 5; ++n2) {
+            const float2 x0 = u[(2 * n2) % 10], x1 = u[(5 + 2 * n2) % 10];
+            a[n2] = cadd(x0, x1);                      // k1 = 0
+            b[n2] = csub(x0, x1);                      // k1 = 1
+        }
+        Dft<5>::run(a);
+        Dft<5>::run(b);
+#pragma unroll
+        for (int k2 = 0; k2 < 5; ++k2) {
+            u[(6 * k2) % 10] = a[k2];
+            u[(5 + 6 * k2) % 10] = b[k2];
+        }
+    }
+};
 template <> struct Dft<16> { __device__ static __forceinline__ void run(float2* u) { DftCT<4, 4>::run(u); } };
 template <> struct Dft<20> { __device__ static __forceinline__ void run(float2* u) { DftCT<4, 5>::run(u); } };
 template <> struct Dft<25> { __device__ static __forceinline__ void run(float2* u) { DftCT<5, 5>::run(u); } };
