@@ -114,3 +114,49 @@ def test_file_to_database(tmp_path):
         assert s > 100 and zero == list(range(s + 20, len(rows), 20))
         assert all(r["cn0"] is None for k, r in enumerate(rows) if k not in zero)       # NaN is stored as NULL
     db.close()
+
+
+def test_pool_results_equal_single_lane():
+    """ColdStartPool: steps in flight on several lanes give what one synchronous pipeline gives."""
+    import torch
+    from sydr_b200 import synth
+    from sydr_b200 import _lib as L
+    from sydr_b200.pipeline import ColdStartPipeline, ColdStartPool
+    fs, nbits, dur = 4e6, 8, 0.25
+    recs = []
+    for seed in (101, 102, 103):
+        sc = synth.make_scenario(fs, nbits, dur, (3, 7, 19, 22)[: 2 + seed % 3], seed, 250.0)
+        recs.append(torch.from_numpy(synth.generate_iq(sc)).pin_memory())
+    kw = dict(fs=fs, nbits=nbits, search_prns=list(range(1, 33)), n_channels=6, max_seconds=dur)
+    single = ColdStartPipeline(**kw)
+    want = []
+    for h in recs:
+        o = single.process_host(h, copy=True)
+        want.append(o)
+    single.close()
+    pool = ColdStartPool(lanes=2, **kw)
+    tickets, got = [], []
+    order = [0, 1, 2, 1, 0, 2, 2]
+    for k in order:
+        if len(tickets) == 2:
+            got.append(pool.result(tickets.pop(0), copy=True))
+        tickets.append(pool.submit_host(recs[k]))
+    import pytest as _pt
+    with _pt.raises(L.SydrError):
+        pool.submit_host(recs[0])                       # both lanes busy
+    while tickets:
+        got.append(pool.result(tickets.pop(0), copy=True))
+    for k, g in zip(order, got):
+        w = want[k]
+        assert np.array_equal(g["peaks"], w["peaks"]) and g["channels"] == w["channels"]
+        assert len(g["epochs"]) == len(w["epochs"]) >= 2
+        for a, b in zip(g["epochs"], w["epochs"]):
+            assert a.tobytes() == b.tobytes()
+    # device-resident submissions
+    d = pool.lanes[0].upload(recs[1])
+    t1 = pool.submit_device(d)
+    t2 = pool.submit_device(d)
+    r1, r2 = pool.result(t1, copy=True), pool.result(t2, copy=True)
+    for a, b, c in zip(r1["epochs"], r2["epochs"], want[1]["epochs"]):
+        assert a.tobytes() == b.tobytes() == c.tobytes()
+    pool.close()

@@ -120,3 +120,64 @@ def test_nav_bits_from_gpu_tracking_recover_the_data_bits():
         agree = (tx == b).mean()
         assert agree == 1.0 or agree == 0.0, (ch["prn"], agree)          # Costas loop: 180 deg ambiguity
     pipe.close()
+
+
+def test_device_handoff_equals_host_handoff():
+    """K-HAND: selection (threshold, best ratios first, at most n_channels, PRN order) and the hand-off
+    scalars of channel_l1ca_borre.py:301-311, bit-identical with the host restatement; idle slots; no peaks."""
+    import torch
+    from sydr_b200 import _lib as L
+    from sydr_b200.engine import make_trk_states
+    from sydr_b200.pipeline import ColdStartPipeline
+    fs = 4e6
+    pipe = ColdStartPipeline(fs, 8, list(range(1, 33)), 5, max_seconds=0.1, doppler_step=250.0)
+    rng = np.random.default_rng(4)
+    for case in range(4):
+        peaks = np.zeros(32, dtype=L.ACQ_PEAK_DTYPE)
+        peaks["prn"] = np.arange(1, 33)
+        peaks["freq_idx"] = rng.integers(0, 41, 32)
+        peaks["code_idx"] = rng.integers(0, 4000, 32)
+        peaks["ratio"] = rng.uniform(1.0, 1.45, 32).astype(np.float32)
+        if case == 0:                                   # more candidates than channels, with a tie at the cut
+            strong = rng.choice(32, 9, replace=False)
+            peaks["ratio"][strong] = rng.uniform(2.0, 9.0, 9).astype(np.float32)
+            peaks["ratio"][strong[:3]] = np.float32(3.25)
+        elif case == 1:                                 # fewer than n_channels
+            peaks["ratio"][[4, 20]] = (np.float32(1.5000001), np.float32(7.0))
+            peaks["ratio"][9] = np.float32(1.5)         # exactly the threshold: not above it
+        elif case == 2:                                 # nothing found
+            pass
+        else:                                           # freq_idx at both ends (Doppler +5000 / -5000, IF + -0.0)
+            peaks["ratio"][[0, 1, 2]] = np.float32(4.0)
+            peaks["freq_idx"][[0, 1, 2]] = (0, 40, 20)
+        pipe.acq.peaks_device().copy_(torch.from_numpy(peaks.view(np.uint8).reshape(-1)).cuda())
+        n = 400000
+        pipe._handoff(n)
+        torch.cuda.synchronize()
+        got = pipe._trk.states()
+        chans = pipe._channels_of(peaks, n)
+        want = make_trk_states(fs, chans) if chans else np.zeros(0, dtype=L.TRK_STATE_DTYPE)
+        assert int(pipe._n_sel.cpu()[0]) == len(chans) <= 5
+        assert [int(p) for p in got["prn"][:len(chans)]] == [c["prn"] for c in chans]
+        assert got[:len(chans)].tobytes() == want.tobytes(), case          # every member, bit for bit
+        assert (got["status"][len(chans):] == 1).all()
+        if case == 1:
+            assert [c["prn"] for c in chans] == [5, 21]
+        if case == 2:
+            assert chans == []
+    pipe.close()
+
+
+def test_pipeline_with_nothing_to_track():
+    """Noise only: the hand-off leaves every slot idle, the tracking launch does nothing, results are empty."""
+    import torch
+    from sydr_b200.pipeline import ColdStartPipeline
+    fs = 4e6
+    rng = np.random.default_rng(8)
+    iq = np.clip(np.round(rng.normal(0, 16, 2 * 200000)), -127, 127).astype(np.int8)
+    pipe = ColdStartPipeline(fs, 8, [1, 2, 3, 4], 4, max_seconds=0.05, threshold=2.5)
+    host = torch.from_numpy(iq).pin_memory()
+    out = pipe.process_host(host)
+    assert out["channels"] == [] and out["epochs"] == [] and len(out["peaks"]) == 4
+    assert (pipe._trk.states()["status"] == 1).all()
+    pipe.close()
