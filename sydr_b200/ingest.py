@@ -308,13 +308,16 @@ class StreamingReceiver:
         return out
 
     # ------------------------------------------------------------------------------------
-    def run_to_database(self, database, skip_samples: int = 0, max_samples: int | None = None, wall_time=None):
+    def run_to_database(self, database, skip_samples: int = 0, max_samples: int | None = None, wall_time=None,
+                        channel_ids: dict | None = None):
         """Whole file into a `DatabaseHandler` (sydr_b200.io.database, the reference's SQLite format):
         one `channel` row and one `acquisition` row per tracked satellite, one `tracking` row per
         channel-epoch, inserted column-wise per chunk while the next chunk is on the GPU.
         `time_sample` is the receiver's sample counter at the millisecond tick on which the reference
         would have emitted the packet (sydr/receiver/receiver.py:120-139, 357-360); `time` is the
-        wall clock (`wall_time()` if given, for reproducible files).  Returns run_all()-style totals."""
+        wall clock (`wall_time()` if given, for reproducible files).  `channel_ids` maps PRN -> channel id
+        when the caller has already registered its channels (no `channel` rows are written then).
+        Returns run_all()-style totals."""
         import time as _time
         from .io.database import cn0_column
         if not self.want_records:
@@ -328,11 +331,13 @@ class StreamingReceiver:
                 chans = res["channels"]
                 done = [0] * len(chans)
                 dwell = self.acq.required_samples
-                for cid, ch in enumerate(chans):
+                cids = [k if channel_ids is None else int(channel_ids[ch["prn"]]) for k, ch in enumerate(chans)]
+                for cid, ch in zip(cids, chans):
                     pk = res["peaks"][[int(p) for p in res["peaks"]["prn"]].index(ch["prn"])]
-                    database.addData("channel", {"id": cid, "physical_id": cid, "system": "GPS",
-                                                 "satellite_id": int(ch["prn"]), "signal": "GPS_L1_CA",
-                                                 "start_time": float(now()), "start_sample": 0})
+                    if channel_ids is None:
+                        database.addData("channel", {"id": cid, "physical_id": cid, "system": "GPS",
+                                                     "satellite_id": int(ch["prn"]), "signal": "GPS_L1_CA",
+                                                     "start_time": float(now()), "start_sample": 0})
                     database.addData("acquisition", {
                         "cid": cid, "carrierFrequency": float(ch["carrier_freq"]), "codeOffset": int(pk["code_idx"]),
                         "frequency_idx": int(pk["freq_idx"]), "code_idx": int(pk["code_idx"]),
@@ -342,16 +347,17 @@ class StreamingReceiver:
             if "epochs" not in res:
                 continue
             sync = self._nav.states()["sync_epoch"] if self._nav is not None else [-1] * len(chans)
-            for cid, rec in enumerate(res["epochs"]):
+            for k, rec in enumerate(res["epochs"]):
+                cid = cids[k]
                 if not len(rec):
                     continue
                 end = (rec["start"] + rec["n"]).astype(np.int64)
                 tick = -(-end // spm) * spm
-                s = int(sync[cid])
+                s = int(sync[k])
                 # a synchronisation found later than this chunk does not reach back into it
-                cn0 = cn0_column(done[cid], len(rec), s if 0 <= s < done[cid] + len(rec) else -1)
+                cn0 = cn0_column(done[k], len(rec), s if 0 <= s < done[k] + len(rec) else -1)
                 database.addTrackingRecords(cid, rec, time=float(now()), time_sample=tick, cn0=cn0)
-                done[cid] += len(rec)
+                done[k] += len(rec)
                 rows += len(rec)
             database.commit()
         return dict(channels=chans, tracking_rows=rows)

@@ -49,6 +49,23 @@ def test_no_cpu_fallback():
         PCPS(np.zeros(4000, dtype=np.complex128), 0.0, 4e6, np.zeros(4000, dtype=complex), 5000, 250, 4000)
 
 
+def test_receiver_needs_the_gpu(tmp_path):
+    """main.py's receiver has no CPU path either: building it without a CUDA device fails loudly."""
+    import configparser
+    lib = L.load()
+    if lib.sydr_device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    from sydr_b200.receiver.receiver_gps_l1ca import ReceiverGPSL1CA
+    cfg = configparser.ConfigParser()
+    assert cfg.read(os.path.join(H.ROOT, "config", "receiver.ini"))
+    cfg["DEFAULT"]["outfolder"] = str(tmp_path)
+    with pytest.raises(L.SydrError):
+        ReceiverGPSL1CA(cfg, overwrite=True)
+    for name in ("channel_GPS_L1CA_borre.ini", "channel_GPS_L1CA_kaplan.ini"):
+        ch = configparser.ConfigParser()
+        assert ch.read(os.path.join(H.ROOT, "config", "channels", name)) and "TRACKING" in ch and "ACQUISITION" in ch
+
+
 def test_product_never_imports_the_oracle():
     pkg = os.path.join(H.ROOT, "sydr_b200")
     for dirpath, _, files in os.walk(pkg):

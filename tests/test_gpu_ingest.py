@@ -160,3 +160,48 @@ def test_pool_results_equal_single_lane():
     for a, b, c in zip(r1["epochs"], r2["epochs"], want[1]["epochs"]):
         assert a.tobytes() == b.tobytes() == c.tobytes()
     pool.close()
+
+
+def test_receiver_from_ini(tmp_path):
+    """main.py's object: ReceiverGPSL1CA built from a receiver.ini, the reference's per-millisecond loop
+    over the batched ChannelManager into the SQLite sink; run_fast() gives the same tracking rows."""
+    import configparser
+    import os
+    from sydr_b200 import synth
+    from sydr_b200.receiver.receiver_gps_l1ca import ReceiverGPSL1CA
+    fs, nbits, ms = 4e6, 8, 300
+    sc = synth.make_scenario(fs, nbits, ms * 1e-3 + 0.13, (3, 7), 95, 250.0)      # 120 ms reader chunks: keep a margin
+    path = str(tmp_path / "rec.bin")
+    synth.write_file(path, synth.generate_iq(sc))
+
+    def config(name):
+        cfg = configparser.ConfigParser()
+        cfg.read(os.path.join(helpers.ROOT, "config", "receiver.ini"))
+        cfg["DEFAULT"].update({"name": name, "ms_to_process": str(ms), "outfolder": str(tmp_path)})
+        cfg["RFSIGNAL"].update({"filepath": path, "sampling_frequency": str(fs), "data_size": str(nbits)})
+        cfg["SATELLITES"]["include_prn"] = "3,7"
+        cfg["CHANNELS"]["gps_l1ca"] = os.path.join(helpers.ROOT, "config", "channels", "channel_GPS_L1CA_borre.ini")
+        return cfg
+
+    a = ReceiverGPSL1CA(config("tick"), overwrite=True)
+    a.run()
+    rows_a = {c: a.database.fetchTracking(c) for c in (0, 1)}
+    chan = a.database.fetchTable("channel")
+    acq = a.database.fetchAcquisition()
+    assert [r["satellite_id"] for r in chan] == [3, 7] and [r["system"] for r in chan] == ["GPS", "GPS"]
+    assert len(acq) == 2 and all(r["peak_ratio"] > 1.5 for r in acq)
+    assert a.samplesCounter == ms * 4000
+    a.close()
+    b = ReceiverGPSL1CA(config("fast"), overwrite=True)
+    b.run_fast(chunk_seconds=0.1)
+    rows_b = {c: b.database.fetchTracking(c) for c in (0, 1)}
+    acq_b = b.database.fetchAcquisition()
+    b.close()
+    assert [r["code_idx"] for r in acq] == [r["code_idx"] for r in acq_b]
+    for c in (0, 1):
+        n = len(rows_a[c])
+        assert n >= ms - 12 and len(rows_b[c]) >= n
+        for key in ("i_prompt", "q_late", "carrier_frequency", "code_frequency", "dll", "pll"):
+            assert [r[key] for r in rows_a[c]] == [r[key] for r in rows_b[c][:n]], key
+        assert [r["time_sample"] for r in rows_a[c]] == [r["time_sample"] for r in rows_b[c][:n]]
+    assert os.path.exists(tmp_path / "tick.db") and os.path.exists(tmp_path / "fast.db")
