@@ -395,3 +395,141 @@ def nav_bits(i_prompts):
     for v in i_prompts:
         o.step(float(v))
     return np.array(o.bits, dtype=np.int8), np.array(o.sums, dtype=np.float64), o.sync_epoch, o
+
+
+# ------------------------------------------------------------------------------------------
+# Kaplan channel: FLL-assisted PLL, lock indicators, C/N0, PULL_IN / WIDE / NARROW machine.
+# ------------------------------------------------------------------------------------------
+GPS_HALF_PI = GPS_PI / 2.0
+W0_BANDWIDTH_1 = 0.25           # sydr/utils/constants.py:80
+W0_BANDWIDTH_2 = 0.53           # sydr/utils/constants.py:81
+W0_SCALE_A2 = 1.414             # sydr/utils/constants.py:83
+PULL_IN, WIDE_TRACK, NARROW_TRACK = 1, 2, 3        # sydr/utils/enumerations.py LoopLockState
+FLAG_CODE_LOCK, FLAG_BIT_SYNC = 1, 2               # sydr/utils/enumerations.py TrackingFlags
+KAPLAN_INI = {   # config/channels/channel_GPS_L1CA_kaplan.ini [TRACKING]
+    "correlator_epl_wide": 0.5, "correlator_epl_narrow": 0.5, "dll_threshold": 10.0, "dll_damping_ratio": 0.7,
+    "dll_noise_bandwidth": 2.0, "dll_loop_gain": 1.0, "dll_pdi": 0.001, "pll_bandwidth_wide": 25.0,
+    "pll_bandwidth_narrow": 15.0, "pll_threshold_wide": 0.5, "pll_threshold_narrow": 0.8,
+    "fll_bandwidth_pullin": 100.0, "fll_bandwidth_wide": 50.0, "fll_bandwidth_narrow": 15.0,
+    "fll_threshold_wide": 0.5, "fll_threshold_narrow": 0.8}
+
+
+def fll_atan(ip, qp, ip_prev, qp_prev, dt):
+    """sydr/dsp/tracking.py:156-176 (FLL_ATAN + phase_unwrap)."""
+    with np.errstate(divide="ignore", invalid="ignore"):
+        e = np.arctan(np.float64(qp) / np.float64(ip)) - np.arctan(np.float64(qp_prev) / np.float64(ip_prev))
+    if np.isnan(e):
+        e = 0.0
+    if e >= GPS_HALF_PI:
+        e = e - GPS_PI
+    elif e <= -GPS_HALF_PI:
+        e = e + GPS_PI
+    return e / dt / GPS_TWO_PI
+
+
+class KaplanTrackOracle:
+    """Scalar state machine of ChannelL1CA_Kaplan.runTracking (sydr/channel/channel_l1ca_kaplan.py:342-619)
+    over a recording held in memory; `corr_override` teacher-forces the six correlator sums."""
+
+    def __init__(self, prn, fs, carrier_freq, start_sample, ini=KAPLAN_INI):
+        c = {k: float(v) for k, v in ini.items()}
+        self.c = c
+        self.fs = float(fs)
+        self.code = padded_code(prn)
+        self.spacings = [-c["correlator_epl_wide"], 0.0, c["correlator_epl_wide"]]
+        self.dll_tau1, self.dll_tau2 = loop_coefficients(c["dll_noise_bandwidth"], c["dll_damping_ratio"],
+                                                         c["dll_loop_gain"])
+        self.code_freq = CODE_FREQ
+        self.carrier_freq = float(carrier_freq)
+        self.rem_code = 0.0
+        self.rem_carrier = 0.0
+        self.code_step = CODE_FREQ / self.fs
+        self.n_req = int(np.ceil((CODE_CHIPS - self.rem_code) / self.code_step))
+        self.cur = int(start_sample)
+        self.ip_prev = self.qp_prev = 0.0
+        self.dll_discrim = 0.0
+        self.fll_lock = self.pll_lock = self.dll_lock = 0.0
+        self.cn0 = 0.0
+        self.pdpn = 0.0
+        self.accum_counter = 0
+        self.vel_memory = 0.0
+        self.fll_bw = c["fll_bandwidth_pullin"]
+        self.pll_bw = c["pll_bandwidth_wide"]
+        self.state = PULL_IN
+        self.flags = 0
+        self.code_counter = 0
+
+    def step(self, rf_all, corr_override=None):
+        c, n = self.c, self.n_req
+        corr = None
+        if corr_override is None or rf_all is not None:
+            corr = epl(rf_all[self.cur:self.cur + n], self.code, self.fs, self.carrier_freq, self.rem_carrier,
+                       self.rem_code, self.code_step, self.spacings)                               # L376-384
+        ie, qe, ip, qp, il, ql = (corr if corr_override is None else [np.float64(v) for v in corr_override])
+        if self.accum_counter == LNAV_MS_PER_BIT:                                                  # L387-389
+            self.accum_counter = 0
+        self.accum_counter += 1                                                                    # L393
+        fll = pll = 0.0                                                                            # L409-432
+        if self.state == PULL_IN:
+            if self.code_counter > 1:
+                fll = fll_atan(ip, qp, self.ip_prev, self.qp_prev, 1e-3)
+        else:
+            fll = fll_atan(ip, qp, self.ip_prev, self.qp_prev, 1e-3)
+            pll = pll_costa(ip, qp)
+        dll = dll_nneml(ie, qe, il, ql)
+        w0f, w0p = self.fll_bw / W0_BANDWIDTH_1, self.pll_bw / W0_BANDWIDTH_2                       # L443-444
+        update = (pll * w0p ** 2 + fll * w0f) * (1 * 1e-3)                                          # tracking.py:270
+        carrier_err = update + self.vel_memory
+        self.vel_memory = update
+        carrier_err += pll * W0_SCALE_A2 * w0p                                                      # tracking.py:275
+        code_err = borre_filter(dll, self.dll_discrim, self.dll_tau1, self.dll_tau2, c["dll_pdi"] * 1)   # L453
+        if self.code_counter != 0:                                                                  # L463-506
+            lock = ip * self.ip_prev - qp * self.qp_prev
+            lock *= np.sign(ip * self.ip_prev + qp * self.qp_prev)
+            lock /= (ip ** 2 + qp ** 2)
+            lock = abs(lock)
+            self.fll_lock = (1 - 0.005) * self.fll_lock + 0.005 * lock                              # lockindicator.py:6-24
+            if self.state > PULL_IN:
+                nbd, nbp = ip ** 2 - qp ** 2, ip ** 2 + qp ** 2
+                self.pll_lock = (1 - 0.005) * self.pll_lock + 0.005 * (nbd / nbp)                   # lockindicator.py:28-44
+            with np.errstate(divide="ignore"):
+                self.pdpn += (ip ** 2 + qp ** 2) / (abs(ip) - abs(qp)) ** 2
+            if self.accum_counter == LNAV_MS_PER_BIT:
+                lam = 1 / (self.pdpn / self.accum_counter)                                          # lockindicator.py:76-99
+                new = lam * (1 / (self.accum_counter * 1e-3))
+                self.cn0 = (1 - 0.1) * self.cn0 + 0.1 * new
+                self.pdpn = 0.0
+            self.dll_lock = self.cn0
+        self.code_counter += 1                                                                      # L515
+        self.dll_discrim = dll
+        self.rem_carrier -= self.carrier_freq * GPS_TWO_PI * n / self.fs                            # L529
+        self.rem_carrier %= GPS_TWO_PI
+        self.code_freq -= code_err
+        self.carrier_freq += carrier_err
+        self.rem_code += n * self.code_step - CODE_CHIPS
+        self.code_step = self.code_freq / self.fs
+        self.cur += n
+        self.n_req = int(np.ceil((CODE_CHIPS - self.rem_code) / self.code_step))
+        # trackingStateUpdate, L545-619
+        if self.state != PULL_IN and self.dll_lock > c["dll_threshold"] and not (self.flags & FLAG_CODE_LOCK):
+            self.flags |= FLAG_CODE_LOCK
+        elif self.dll_lock < c["dll_threshold"] and (self.flags & FLAG_CODE_LOCK):
+            self.flags ^= FLAG_CODE_LOCK
+        if (self.flags & FLAG_CODE_LOCK) and not (self.flags & FLAG_BIT_SYNC):
+            if np.sign(self.ip_prev) != np.sign(ip):
+                self.flags |= FLAG_BIT_SYNC
+                self.accum_counter = 1
+                self.pdpn = 0.0
+        self.ip_prev, self.qp_prev = ip, qp
+        if self.state != NARROW_TRACK and self.fll_lock >= c["fll_threshold_narrow"] \
+                and self.pll_lock >= c["pll_threshold_narrow"]:
+            self.state, self.fll_bw, self.pll_bw = NARROW_TRACK, c["fll_bandwidth_narrow"], c["pll_bandwidth_narrow"]
+        elif self.state != WIDE_TRACK and c["fll_threshold_wide"] <= self.fll_lock < c["fll_threshold_narrow"]:
+            self.state, self.fll_bw, self.pll_bw = WIDE_TRACK, c["fll_bandwidth_wide"], c["pll_bandwidth_wide"]
+        elif self.state != PULL_IN and self.fll_lock <= c["fll_threshold_wide"]:
+            self.state, self.fll_bw, self.pll_bw = PULL_IN, c["fll_bandwidth_pullin"], 0.0
+        return dict(corr=corr, dll=dll, pll=pll, fll=fll, carrier_frequency=self.carrier_freq,
+                    code_frequency=self.code_freq, carrier_frequency_error=carrier_err, code_frequency_error=code_err,
+                    cn0=self.cn0, pll_lock=self.pll_lock, fll_lock=self.fll_lock, lock_state=self.state,
+                    flags=self.flags, rem_code=self.rem_code, rem_carrier=self.rem_carrier, n=n, n_req=self.n_req,
+                    cur=self.cur)

@@ -138,6 +138,25 @@ def test_nav_bit_oracle_matches_reference_channel(golden):
     assert sync > 100 and len(b) == len(s)
 
 
+def test_kaplan_loop_oracle_matches_reference_channel(golden):
+    """KaplanTrackOracle (FLL-assisted PLL, lock indicators, C/N0, PULL_IN/WIDE/NARROW, code lock, bit
+    sync) teacher-forced with the live reference channel's correlator sums: every packet field of all
+    2590 epochs, exactly."""
+    g = golden("kaplan.npz")
+    cols = dict(dll=7, pll=8, fll=9, carrier_frequency=10, code_frequency=11, carrier_frequency_error=12,
+                code_frequency_error=13, cn0=14, pll_lock=15, fll_lock=16, lock_state=17, rem_code=19, rem_carrier=20,
+                n_req=21)
+    for prn in (int(p) for p in g["prns"]):
+        ref, ra = g[f"trk_{prn}"], g[f"acq_{prn}"]
+        o = O.KaplanTrackOracle(prn, float(g["meta"][0]), float(ra[4]), 0)
+        for k in range(len(ref)):
+            r = o.step(None, corr_override=ref[k, 1:7])
+            for name, col in cols.items():
+                assert float(r[name]) == ref[k, col], (prn, k, name)
+            assert (r["flags"] & 3) == (int(ref[k, 18]) & 3), (prn, k)
+        assert {1, 2, 3} <= set(ref[:, 17].astype(int))
+
+
 def test_against_compiled_reference_c(golden):
     """getCorrelator of the reference's own tracking.c (compiled by oracle/Makefile) vs the oracle."""
     lib = ctypes.CDLL(REF_SO)
