@@ -240,6 +240,48 @@ int sydr_acq_handoff(const sydr_acq_peak* d_peaks, int n_prn, double inter_freq,
                      long long iq_len, sydr_trk_state* d_states, int max_channels, int* d_n_selected,
                      void* stream);
 
+/* ------------------------------------------------------------------ Kaplan loops ------ */
+/* Loop closure of ChannelL1CA_Kaplan on the device (sydr/channel/channel_l1ca_kaplan.py:342-619):
+ * FLL_ATAN + PLL_costa discriminators, FLLassistedPLL_2ndOrder (sydr/dsp/tracking.py:156-176,
+ * 246-279), FLL_Lock_Borre / PLL_Lock_Borre / CN0_Beaulieu (sydr/dsp/lockindicator.py:6-99), code
+ * lock, bit synchronisation and the PULL_IN / WIDE_TRACK / NARROW_TRACK machine with its
+ * bandwidth switching.  The code loop (DLL_NNEML + BorreLoopFilter) and the NCO members are those
+ * of sydr_trk_state.  One record per channel next to its sydr_trk_state. */
+typedef struct {
+    /* [TRACKING] of channel_GPS_L1CA_kaplan.ini */
+    double  fll_bw_pullin, fll_bw_wide, fll_bw_narrow;
+    double  pll_bw_wide, pll_bw_narrow;
+    double  fll_thr_wide, fll_thr_narrow, pll_thr_narrow, dll_threshold;
+    /* channel members */
+    double  ip_prev, qp_prev;           /* iPromptPrev, qPromptPrev                              */
+    double  fll_lock, pll_lock;         /* fllLockIndicator, pllLockIndicator                    */
+    double  cn0, pdpn;                  /* cn0 (= dllLockIndicator), cn0_PdPnRatio               */
+    double  vel_memory;                 /* fll_vel_memory                                        */
+    double  fll_bw, pll_bw;             /* fllBandwidth, pllBandwidth (current)                  */
+    int32_t accum_counter;              /* correlatorsAccumCounter                               */
+    int32_t lock_state;                 /* LoopLockState: 1 PULL_IN, 2 WIDE_TRACK, 3 NARROW_TRACK */
+    int32_t flags;                      /* TrackingFlags bits: 1 CODE_LOCK, 2 BIT_SYNC           */
+    int32_t reserved;
+    int64_t code_counter;               /* codeCounter                                           */
+} sydr_kaplan_state;        /* 168 bytes */
+
+/* What the Kaplan TRACKING_UPDATE packet carries beyond sydr_trk_epoch (there: dll = code filter
+ * output = code_frequency_error, code_err = DLL discriminator = "dll", pll = carrier filter output =
+ * carrier_frequency_error, carrier_err = PLL discriminator = "pll"). */
+typedef struct {
+    double  fll;                        /* FLL discriminator                                     */
+    double  cn0, fll_lock, pll_lock;
+    int32_t lock_state, flags;
+} sydr_kaplan_epoch;        /* 40 bytes */
+
+/* sydr_trk_run with the Kaplan loop closure: d_kstates[n_channels] in/out,
+ * d_kout[n_channels][max_epochs] indexed like d_out.  Both correlator spacings of the channel
+ * configuration (wide / narrow) must be equal, as in the reference's ini. */
+int sydr_trk_run_kaplan(const void* d_iq, int iq_dtype, long long iq_alloc_samples, double fs,
+                        sydr_trk_state* d_states, sydr_kaplan_state* d_kstates, int n_channels,
+                        sydr_trk_epoch* d_out, sydr_kaplan_epoch* d_kout, int max_epochs, int* d_nepochs,
+                        const sydr_trk_config* cfg, void* stream);
+
 /* ------------------------------------------------------------------ nav bits --------- */
 /* Bit synchronisation + navigation-bit accumulation on the device (K-NAV): the scalar state
  * machine ChannelL1CA runs on every tracking result (channel_l1ca_borre.py:398-413 bit-sync

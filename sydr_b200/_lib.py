@@ -79,6 +79,14 @@ TRK_STATE_DTYPE = np.dtype([("iq_base", "<i8"), ("iq_len", "<i8"), ("cur", "<i8"
 TRK_EPOCH_DTYPE = np.dtype([("corr", "<f8", (6,)), ("dll", "<f8"), ("pll", "<f8"), ("carrier_freq", "<f8"),
                             ("code_freq", "<f8"), ("code_err", "<f8"), ("carrier_err", "<f8"),
                             ("start", "<f8"), ("n", "<f8"), ("rem_code", "<f8"), ("rem_carrier", "<f8")])
+KAPLAN_STATE_DTYPE = np.dtype([(n, "<f8") for n in (
+    "fll_bw_pullin", "fll_bw_wide", "fll_bw_narrow", "pll_bw_wide", "pll_bw_narrow", "fll_thr_wide", "fll_thr_narrow",
+    "pll_thr_narrow", "dll_threshold", "ip_prev", "qp_prev", "fll_lock", "pll_lock", "cn0", "pdpn", "vel_memory",
+    "fll_bw", "pll_bw")] + [("accum_counter", "<i4"), ("lock_state", "<i4"), ("flags", "<i4"), ("reserved", "<i4"),
+                           ("code_counter", "<i8")])
+KAPLAN_EPOCH_DTYPE = np.dtype([("fll", "<f8"), ("cn0", "<f8"), ("fll_lock", "<f8"), ("pll_lock", "<f8"),
+                               ("lock_state", "<i4"), ("flags", "<i4")])
+assert KAPLAN_STATE_DTYPE.itemsize == 168 and KAPLAN_EPOCH_DTYPE.itemsize == 40
 NAV_STATE_DTYPE = np.dtype([("code_counter", "<i8"), ("sync_epoch", "<i8"), ("prev_iprompt", "<f8"),
                             ("row19", "<f8"), ("nav_sum", "<f8"), ("nav_count", "<i4"), ("n_bits", "<i4")])
 assert NAV_STATE_DTYPE.itemsize == 48
@@ -112,6 +120,7 @@ SIGNATURES = {
     "sydr_peak_compare": (_i, [_vp, _i, _i, _i, _ip, _ip, _dp]),
     "sydr_epl_batch": (_i, [_vp, _i, _ll, _d, _vp, _i, _vp, _vp]),
     "sydr_trk_run": (_i, [_vp, _i, _ll, _d, _vp, _i, _vp, _i, _vp, _vp, _vp]),
+    "sydr_trk_run_kaplan": (_i, [_vp, _i, _ll, _d, _vp, _vp, _i, _vp, _vp, _i, _vp, _vp, _vp]),
     "sydr_trk_profile_buffer": (_i, [_vp]),
     "sydr_trk_set_mode": (_i, [_i]),
     "sydr_trk_state_init": (_i, [_vp, _i, _d, _d, _ll] + [_d] * 11),

@@ -851,6 +851,8 @@ struct TrkParams {
     double acc_inv;          // 1 / acc_scale
     int resume;              // follow-up of a LEAN launch: continue the record rows, serve kNeedGeneral channels
     long long* prof;         // optional [n_channels][16] phase cycle counters of thread 0 (NULL = off)
+    sydr_kaplan_state* kstates;   // Kaplan loop closure (KAP instantiation): per-channel state and per-epoch extras
+    sydr_kaplan_epoch* kout;
 };
 
 struct EpochCtl {            // published by warps 0 / 1 for every epoch
@@ -883,6 +885,7 @@ struct TrkSharedT {          // static shared memory of the closed-loop kernel
     int n_hist[2];           // samples of epoch e (index e & 1), for the carrier warp
     int rec_base;            // index of this call's first record in the channel's output row
     int status;
+    sydr_kaplan_state kcfg;  // Kaplan loop closure: the channel's configuration and state as loaded / to store
     int seg_ok;              // segment path usable for this channel (spacings on the half-chip lattice)
     int seg_q[3];            // tap offsets in half chips
     uint32_t segtab[NTAB];   // sign bytes of the three taps per lattice index
@@ -1054,6 +1057,119 @@ __device__ __forceinline__ void carrier_close(SH& sh, CarrierState& st, double c
     }
 }
 
+// ---- Kaplan loop closure (warp 1) ----------------------------------------------------------------
+// channel_l1ca_kaplan.py:342-619 after the correlators: discriminators, FLL-assisted PLL filter, lock
+// indicators, C/N0, NCO, code lock / bit synchronisation, lock-state machine.  IEEE operations in the
+// reference's order, no contraction: the same values as the Python floats (atan to 2 ulp).
+struct KaplanRegs {                 // mutable members, registers of warp 1
+    double ip_prev, qp_prev, fll_lock, pll_lock, cn0, pdpn, vel_memory, fll_bw, pll_bw;
+    int accum_counter, lock_state, flags;
+    long long code_counter;
+};
+__device__ __forceinline__ double np_sign(double x) { return (x > 0.0) ? 1.0 : ((x < 0.0) ? -1.0 : x); }   // 0 -> 0, nan -> nan
+
+// remainingCarrier after the epoch, channel_l1ca_kaplan.py:529-530 (GPS value of two pi, Python float %)
+template <class SH>
+__device__ __forceinline__ double carrier_pre_kaplan(const SH& sh, const CarrierState& st, int n_epoch) {
+    const double twopi = kGpsPi * 2.0;
+    double rc = dsub(st.rem_carrier, __ddiv_rn(dmul(dmul(st.carrier_freq, twopi), i2d(n_epoch)), sh.K.fs));
+    const double q = floor(rc * (1.0 / (kGpsPi * 2.0)));
+    rc = fma(-q, twopi, rc);
+    if (rc < 0.0) rc += twopi;
+    if (rc >= twopi) rc -= twopi;
+    return rc;
+}
+
+__device__ __forceinline__ double fll_atan(double ip, double qp, double ipp, double qpp) {      // tracking.py:156-176
+    double e = atan(__ddiv_rn(qp, ip)) - atan(__ddiv_rn(qpp, ipp));
+    if (isnan(e)) e = 0.0;
+    const double half_pi = kGpsPi / 2.0;
+    if (e >= half_pi) e = dsub(e, kGpsPi);
+    else if (e <= -half_pi) e = dadd(e, kGpsPi);
+    return __ddiv_rn(__ddiv_rn(e, 1e-3), kGpsPi * 2.0);
+}
+
+template <class SH>
+__device__ __forceinline__ void carrier_close_kaplan(SH& sh, CarrierState& st, KaplanRegs& k, double ck, double rc,
+                                                     sydr_trk_epoch* rec, sydr_kaplan_epoch* krec, int lane) {
+    const unsigned full = 0xffffffffu;
+    const double ip = __shfl_sync(full, ck, 2), qp = __shfl_sync(full, ck, 3);
+    const sydr_kaplan_state& c = sh.kcfg;
+    // runCorrelators: the 20 ms accumulator counter (L387-393)
+    if (k.accum_counter == 20) k.accum_counter = 0;
+    k.accum_counter += 1;
+    // runDiscriminators (L407-432)
+    double fll = 0.0, pll = 0.0;
+    if (k.lock_state == 1) {
+        if (k.code_counter > 1) fll = fll_atan(ip, qp, k.ip_prev, k.qp_prev);
+    } else {
+        fll = fll_atan(ip, qp, k.ip_prev, k.qp_prev);
+        pll = __ddiv_rn(atan(__ddiv_rn(qp, ip)), kGpsPi * 2.0);                          // PLL_costa
+    }
+    // FLLassistedPLL_2ndOrder (tracking.py:246-279), w0f = B_fll / 0.25, w0p = B_pll / 0.53
+    const double w0f = __ddiv_rn(k.fll_bw, 0.25), w0p = __ddiv_rn(k.pll_bw, 0.53);
+    const double update = dmul(dadd(dmul(pll, dmul(w0p, w0p)), dmul(fll, w0f)), dmul(1.0, 1e-3));
+    double cerr = dadd(update, k.vel_memory);
+    k.vel_memory = update;
+    cerr = dadd(cerr, dmul(dmul(pll, 1.414), w0p));
+    // runLoopIndicators (L460-508)
+    if (k.code_counter != 0) {
+        const double i2 = dmul(ip, ip), q2 = dmul(qp, qp);
+        double lock = dsub(dmul(ip, k.ip_prev), dmul(qp, k.qp_prev));
+        lock = dmul(lock, np_sign(dadd(dmul(ip, k.ip_prev), dmul(qp, k.qp_prev))));
+        lock = fabs(__ddiv_rn(lock, dadd(i2, q2)));
+        k.fll_lock = dadd(dmul(dsub(1.0, 0.005), k.fll_lock), dmul(0.005, lock));
+        if (k.lock_state > 1)
+            k.pll_lock = dadd(dmul(dsub(1.0, 0.005), k.pll_lock), dmul(0.005, __ddiv_rn(dsub(i2, q2), dadd(i2, q2))));
+        const double d = dsub(fabs(ip), fabs(qp));
+        k.pdpn = dadd(k.pdpn, __ddiv_rn(dadd(i2, q2), dmul(d, d)));
+        if (k.accum_counter == 20) {                                                     // CN0_Beaulieu, alpha = 0.1
+            const double lam = __ddiv_rn(1.0, __ddiv_rn(k.pdpn, 20.0));
+            const double neu = dmul(lam, __ddiv_rn(1.0, dmul(20.0, 1e-3)));
+            k.cn0 = dadd(dmul(dsub(1.0, 0.1), k.cn0), dmul(0.1, neu));
+            k.pdpn = 0.0;
+        }
+    }
+    // postTrackingUpdate (L512-541): carrier part
+    k.code_counter += 1;
+    st.rem_carrier = rc;
+    st.carrier_freq = dadd(st.carrier_freq, cerr);
+    st.nco_carrier_err = pll;
+    st.nco_carrier = cerr;
+    // trackingStateUpdate (L545-619)
+    if (k.lock_state != 1 && k.cn0 > c.dll_threshold && !(k.flags & 1)) k.flags |= 1;
+    else if (k.cn0 < c.dll_threshold && (k.flags & 1)) k.flags ^= 1;
+    if ((k.flags & 1) && !(k.flags & 2) && np_sign(k.ip_prev) != np_sign(ip)) {
+        k.flags |= 2;
+        k.accum_counter = 1;
+        k.pdpn = 0.0;
+    }
+    k.ip_prev = ip;
+    k.qp_prev = qp;
+    if (k.lock_state != 3 && k.fll_lock >= c.fll_thr_narrow && k.pll_lock >= c.pll_thr_narrow) {
+        k.lock_state = 3; k.fll_bw = c.fll_bw_narrow; k.pll_bw = c.pll_bw_narrow;
+    } else if (k.lock_state != 2 && k.fll_lock >= c.fll_thr_wide && k.fll_lock < c.fll_thr_narrow) {
+        k.lock_state = 2; k.fll_bw = c.fll_bw_wide; k.pll_bw = c.pll_bw_wide;
+    } else if (k.lock_state != 1 && k.fll_lock <= c.fll_thr_wide) {
+        k.lock_state = 1; k.fll_bw = c.fll_bw_pullin; k.pll_bw = 0.0;
+    }
+    if (rec != nullptr) {                        // lane 7 carrier filter output, 8 carrier_freq, 11 PLL discriminator, 15 rem_carrier
+        double v = cerr;
+        v = (lane == 8) ? st.carrier_freq : v;
+        v = (lane == 11) ? pll : v;
+        v = (lane == 15) ? rc : v;
+        if ((0x8980u >> lane) & 1u) reinterpret_cast<double*>(rec)[lane] = v;
+        if (lane >= 16 && lane < 20) {
+            double w = fll;
+            w = (lane == 17) ? k.cn0 : w;
+            w = (lane == 18) ? k.fll_lock : w;
+            w = (lane == 19) ? k.pll_lock : w;
+            reinterpret_cast<double*>(krec)[lane - 16] = w;
+        }
+        if (lane == 20) { krec->lock_state = k.lock_state; krec->flags = k.flags; }
+    }
+}
+
 // One channel = one CTA or one cluster of S CTAs; W warps per CTA.  Per epoch:
 //   (A) block barrier: the epoch constants published by warps 0 / 1 are visible;
 //   (B) every warp correlates its chunks of the staged window, reduces its six sums with
@@ -1069,7 +1185,9 @@ __device__ __forceinline__ void carrier_close(SH& sh, CarrierState& st, double c
 // then repeats the launch with the general instantiation (sydr_trk_run).
 // PROF = phase cycle counters compiled in (diagnostics instantiation; the counters sit on the serial
 // chain, so the production instantiation does not carry them).
-template <int DT, int VPC, bool TMA, bool LEAN, bool PROF = false>
+// KAP = the carrier warp closes the Kaplan loops (FLL-assisted PLL, lock indicators, C/N0, lock-state
+// machine) instead of the Borre PLL; the code loop and everything else are shared.
+template <int DT, int VPC, bool TMA, bool LEAN, bool PROF = false, bool KAP = false>
 __global__ void __launch_bounds__(LEAN ? kLeanThreads : kTrkMaxThreads, LEAN ? 3 : 1) trk_borre_kernel(const TrkParams P) {
     constexpr int SPV = IqTraits<DT>::SPV, BPS = IqTraits<DT>::BPS;
     constexpr int C = SPV * VPC;
@@ -1108,6 +1226,7 @@ __global__ void __launch_bounds__(LEAN ? kLeanThreads : kTrkMaxThreads, LEAN ? 3
         sh.K.dll_c1 = g.dll_tau2 / g.dll_tau1; sh.K.dll_c2 = g.dll_pdi / g.dll_tau1;
         sh.K.pll_c1 = g.pll_tau2 / g.pll_tau1; sh.K.pll_c2 = g.pll_pdi / g.pll_tau1;
         sh.status = sh.cfgs.status;
+        if (KAP) sh.kcfg = P.kstates[ch];
         sh.seg_ok = (NV > 0 && P.seg) ? (seg_tap_offsets(sh.cfgs.spacing, sh.seg_q) ? 1 : 0) : 0;
         for (int k = 0; k < 16; ++k) sh.pc[k] = 0;
         mbar_init(&sh.bar_data[0], 1);
@@ -1148,6 +1267,15 @@ __global__ void __launch_bounds__(LEAN ? kLeanThreads : kTrkMaxThreads, LEAN ? 3
     // loop state lives in registers of its owning warp (warp 0: code, warp 1: carrier)
     CodeState sc = sh.sc;
     CarrierState sk = sh.sk;
+    KaplanRegs kr = {};
+    if (KAP) {
+        const sydr_kaplan_state& g = sh.kcfg;
+        kr.ip_prev = g.ip_prev; kr.qp_prev = g.qp_prev; kr.fll_lock = g.fll_lock; kr.pll_lock = g.pll_lock;
+        kr.cn0 = g.cn0; kr.pdpn = g.pdpn; kr.vel_memory = g.vel_memory; kr.fll_bw = g.fll_bw; kr.pll_bw = g.pll_bw;
+        kr.accum_counter = g.accum_counter; kr.lock_state = g.lock_state; kr.flags = g.flags;
+        kr.code_counter = g.code_counter;
+    }
+    sydr_kaplan_epoch* kout_row = (KAP && rank == 0) ? P.kout + (long long)ch * P.max_epochs + sh.rec_base : nullptr;
     int status = sh.cfgs.status;                   // != 0: aborted earlier (< 0) or idle slot (> 0): no epochs
     int epoch = 0;
     // loop-invariant limits of the stop test
@@ -1328,7 +1456,7 @@ __global__ void __launch_bounds__(LEAN ? kLeanThreads : kTrkMaxThreads, LEAN ? 3
             CodePre cpre = {0.0, 0.0};
             double rc_next = 0.0;
             if (warp == 0) cpre = code_pre(sc);
-            else rc_next = carrier_pre(sh, sk, sh.n_hist[e & 1]);
+            else rc_next = KAP ? carrier_pre_kaplan(sh, sk, sh.n_hist[e & 1]) : carrier_pre(sh, sk, sh.n_hist[e & 1]);
             mbar_wait(&sh.bar_gather[slot], (e >> 1) & 1);       // st.async data is visible once the phase completes
             SYDR_TICK(5)                               // all-gather: wait for the slowest warp of the cluster
             SYDR_TICK1(10)                             // carrier warp: everything up to the gather
@@ -1337,6 +1465,7 @@ __global__ void __launch_bounds__(LEAN ? kLeanThreads : kTrkMaxThreads, LEAN ? 3
             SYDR_TICK1(11)
             sydr_trk_epoch* rec = out_row ? out_row + e : nullptr;
             if (warp == 0) code_close(sh, sc, status, ck, rec, lane, cpre);
+            else if (KAP) carrier_close_kaplan(sh, sk, kr, ck, rc_next, rec, kout_row ? kout_row + e : nullptr, lane);
             else carrier_close(sh, sk, ck, rc_next, rec, lane);
             SYDR_TICK(6)                               // loop closure
             SYDR_TICK1(12)
@@ -1348,6 +1477,13 @@ __global__ void __launch_bounds__(LEAN ? kLeanThreads : kTrkMaxThreads, LEAN ? 3
 
     if (warp == 0 && lane == 0) sh.sc = sc;
     if (warp == 1 && lane == 0) sh.sk = sk;
+    if (KAP && warp == 1 && lane == 0) {
+        sydr_kaplan_state& g = sh.kcfg;
+        g.ip_prev = kr.ip_prev; g.qp_prev = kr.qp_prev; g.fll_lock = kr.fll_lock; g.pll_lock = kr.pll_lock;
+        g.cn0 = kr.cn0; g.pdpn = kr.pdpn; g.vel_memory = kr.vel_memory; g.fll_bw = kr.fll_bw; g.pll_bw = kr.pll_bw;
+        g.accum_counter = kr.accum_counter; g.lock_state = kr.lock_state; g.flags = kr.flags;
+        g.code_counter = kr.code_counter;
+    }
     __syncthreads();
     if (prof && rank == 0) {
         for (int k = 0; k < 15; ++k) P.prof[ch * 16 + k] = sh.pc[k];
@@ -1360,6 +1496,7 @@ __global__ void __launch_bounds__(LEAN ? kLeanThreads : kTrkMaxThreads, LEAN ? 3
         gst->nco_code = sh.sc.nco_code; gst->nco_code_err = sh.sc.nco_code_err;
         gst->nco_carrier = sh.sk.nco_carrier; gst->nco_carrier_err = sh.sk.nco_carrier_err;
         gst->status = sh.status;
+        if (KAP) P.kstates[ch] = sh.kcfg;
         P.nepochs[ch] = sh.rec_base + epoch;
     }
     if (S > 1) cluster_sync_all();                  // nobody leaves while peers may still write here
@@ -1392,6 +1529,8 @@ int launch_trk(const TrkParams& P, int n_channels, int cluster, int threads, int
     constexpr bool HAS_LEAN = SegTraits<DT, VPC>::NV > 0;
     auto kern = P.use_tma ? trk_borre_kernel<DT, VPC, true, false> : trk_borre_kernel<DT, VPC, false, false>;
     if (P.prof != nullptr) kern = P.use_tma ? trk_borre_kernel<DT, VPC, true, false, true> : trk_borre_kernel<DT, VPC, false, false, true>;
+    if (P.kstates != nullptr)
+        kern = P.use_tma ? trk_borre_kernel<DT, VPC, true, false, false, true> : trk_borre_kernel<DT, VPC, false, false, false, true>;
     size_t smem_launch = smem;
     if constexpr (HAS_LEAN) {
         if (lean) {
@@ -1491,9 +1630,30 @@ int sydr_epl_batch(const void* d_iq, int iq_dtype, long long iq_len, double fs, 
     return SYDR_ERR_UNSUPPORTED;
 }
 
+static int trk_run_impl(const void* d_iq, int iq_dtype, long long iq_alloc_samples, double fs, sydr_trk_state* d_states,
+                        int n_channels, sydr_trk_epoch* d_out, int max_epochs, int* d_nepochs, const sydr_trk_config* cfg,
+                        void* stream, sydr_kaplan_state* d_kstates, sydr_kaplan_epoch* d_kout);
+
 int sydr_trk_run(const void* d_iq, int iq_dtype, long long iq_alloc_samples, double fs, sydr_trk_state* d_states,
                  int n_channels, sydr_trk_epoch* d_out, int max_epochs, int* d_nepochs, const sydr_trk_config* cfg,
                  void* stream) {
+    return trk_run_impl(d_iq, iq_dtype, iq_alloc_samples, fs, d_states, n_channels, d_out, max_epochs, d_nepochs, cfg,
+                        stream, nullptr, nullptr);
+}
+
+int sydr_trk_run_kaplan(const void* d_iq, int iq_dtype, long long iq_alloc_samples, double fs, sydr_trk_state* d_states,
+                        sydr_kaplan_state* d_kstates, int n_channels, sydr_trk_epoch* d_out, sydr_kaplan_epoch* d_kout,
+                        int max_epochs, int* d_nepochs, const sydr_trk_config* cfg, void* stream) {
+    SYDR_REQUIRE(d_kstates && d_kout, SYDR_ERR_ARG, "NULL pointer");
+    return trk_run_impl(d_iq, iq_dtype, iq_alloc_samples, fs, d_states, n_channels, d_out, max_epochs, d_nepochs, cfg,
+                        stream, d_kstates, d_kout);
+}
+
+}  // extern "C"
+
+static int trk_run_impl(const void* d_iq, int iq_dtype, long long iq_alloc_samples, double fs, sydr_trk_state* d_states,
+                        int n_channels, sydr_trk_epoch* d_out, int max_epochs, int* d_nepochs, const sydr_trk_config* cfg,
+                        void* stream, sydr_kaplan_state* d_kstates, sydr_kaplan_epoch* d_kout) {
     SYDR_REQUIRE(d_iq && d_states && d_out && d_nepochs, SYDR_ERR_ARG, "NULL pointer");
     SYDR_REQUIRE(((uintptr_t)d_iq & 15) == 0, SYDR_ERR_ARG, "d_iq must be 16-byte aligned");
     SYDR_REQUIRE(fs >= 2.0e6, SYDR_ERR_UNSUPPORTED, "fs %.0f Hz below the supported 2 MHz", fs);
@@ -1552,7 +1712,7 @@ int sydr_trk_run(const void* d_iq, int iq_dtype, long long iq_alloc_samples, dou
     const double half_chip = 0.5 * fs / kCodeFreq;
     const bool seg_fits = nv > 0 && g_trk_mode == 0 && half_chip >= 2 * nv - 2 + 0.05 && half_chip <= 2 * nv - 1 - 0.05;
     const bool auto_shape = !cfg || cfg->cluster <= 0;
-    const bool lean = seg_fits && ((auto_shape && cluster == 1) ||
+    const bool lean = d_kstates == nullptr && seg_fits && ((auto_shape && cluster == 1) ||
                                    (!auto_shape && cluster == 1 && !use_tma && threads > 0 && threads <= kLeanThreads &&
                                     (threads & (threads - 1)) == 0));   // power of two: rounds by shift
 
@@ -1586,6 +1746,8 @@ int sydr_trk_run(const void* d_iq, int iq_dtype, long long iq_alloc_samples, dou
     };
     P.resume = 0;
     P.prof = g_trk_prof;
+    P.kstates = d_kstates;
+    P.kout = d_kout;
     cudaStream_t s = (cudaStream_t)stream;
     if (lean) {
         TrkParams PL = P;
@@ -1602,6 +1764,8 @@ int sydr_trk_run(const void* d_iq, int iq_dtype, long long iq_alloc_samples, dou
     set_scale(P, cluster * (threads / 32));
     return dispatch_trk(iq_dtype, vpc, P, n_channels, cluster, threads, 0, s);
 }
+
+extern "C" {
 
 int sydr_trk_state_init(sydr_trk_state* h, int prn, double fs, double carrier_freq, long long start_sample,
                         double dll_bw, double dll_damp, double dll_gain, double dll_pdi, double pll_bw,

@@ -370,3 +370,75 @@ class NavBitEngine:
         bits = self._bits.view(self.n_ch, self.max_bits)[:, :mx].cpu().numpy()
         sums = self._sums.view(self.n_ch, self.max_bits)[:, :mx].cpu().numpy() if want_sums else None
         return [(bits[c, :nb[c]].copy(), sums[c, :nb[c]].copy() if want_sums else None) for c in range(self.n_ch)]
+
+
+# ======================================================================================
+KAPLAN_DEFAULTS = dict(  # config/channels/channel_GPS_L1CA_kaplan.ini [TRACKING]
+    correlator_epl_wide=0.5, correlator_epl_narrow=0.5, dll_threshold=10.0, dll_damping_ratio=0.7,
+    dll_noise_bandwidth=2.0, dll_loop_gain=1.0, dll_pdi=0.001, pll_bandwidth_wide=25.0, pll_bandwidth_narrow=15.0,
+    pll_threshold_wide=0.5, pll_threshold_narrow=0.8, fll_bandwidth_pullin=100.0, fll_bandwidth_wide=50.0,
+    fll_bandwidth_narrow=15.0, fll_threshold_wide=0.5, fll_threshold_narrow=0.8,
+)
+
+
+def make_kaplan_states(fs, channels, cfg=None):
+    """Initial states of ChannelL1CA_Kaplan channels when tracking starts (channel_l1ca_kaplan.py:262-340):
+    (sydr_trk_state array, sydr_kaplan_state array)."""
+    c = dict(KAPLAN_DEFAULTS)
+    if cfg:
+        c.update({k: float(v) for k, v in cfg.items() if k in c})
+    if c["correlator_epl_wide"] != c["correlator_epl_narrow"]:
+        raise L.SydrError("the device Kaplan loop needs equal wide and narrow correlator spacings "
+                          "(use the host channel class otherwise)")
+    channels = list(channels)
+    w = c["correlator_epl_wide"]
+    st = make_trk_states(fs, channels, dict(correlator_early=-w, correlator_prompt=0.0, correlator_late=w,
+                                            dll_damping_ratio=c["dll_damping_ratio"],
+                                            dll_noise_bandwidth=c["dll_noise_bandwidth"],
+                                            dll_loop_gain=c["dll_loop_gain"], dll_pdi=c["dll_pdi"]))
+    ks = np.zeros(len(channels), dtype=L.KAPLAN_STATE_DTYPE)
+    ks["fll_bw_pullin"], ks["fll_bw_wide"], ks["fll_bw_narrow"] = (c["fll_bandwidth_pullin"], c["fll_bandwidth_wide"],
+                                                                   c["fll_bandwidth_narrow"])
+    ks["pll_bw_wide"], ks["pll_bw_narrow"] = c["pll_bandwidth_wide"], c["pll_bandwidth_narrow"]
+    ks["fll_thr_wide"], ks["fll_thr_narrow"] = c["fll_threshold_wide"], c["fll_threshold_narrow"]
+    ks["pll_thr_narrow"], ks["dll_threshold"] = c["pll_threshold_narrow"], c["dll_threshold"]
+    ks["fll_bw"], ks["pll_bw"] = c["fll_bandwidth_pullin"], c["pll_bandwidth_wide"]      # L326-327
+    ks["lock_state"] = 1                                                                 # PULL_IN, L333
+    return st, ks
+
+
+class KaplanTrackingEngine(TrackingEngine):
+    """Closed-loop tracking with the Kaplan loop closure on the device (K-TRK, KAP instantiation):
+    FLL-assisted PLL, lock indicators, C/N0, code lock / bit sync, PULL_IN -> WIDE -> NARROW."""
+
+    def __init__(self, fs, states: np.ndarray, kstates: np.ndarray, max_epochs: int, cluster=0, threads=0,
+                 use_tma=True, device=None):
+        super().__init__(fs, states, max_epochs, cluster=cluster, threads=threads, use_tma=use_tma, device=device)
+        ks = np.ascontiguousarray(kstates)
+        assert ks.dtype == L.KAPLAN_STATE_DTYPE and len(ks) == self.n_ch
+        self._kstates = torch.from_numpy(ks.view(np.uint8).reshape(-1).copy()).to(self.device)
+        self._kout = torch.zeros(self.n_ch * self.max_epochs * 40, dtype=torch.uint8, device=self.device)
+
+    def launch(self, iq_dev: torch.Tensor, stream=None, iq_len: int = 0, append: bool = False, iq_base=None):
+        iq_dev = ensure_padded(iq_dev)
+        self.cfg.iq_len = int(iq_len)
+        self.cfg.append = 1 if append else 0
+        self.cfg.use_iq_base = 0 if iq_base is None else 1
+        self.cfg.iq_base = 0 if iq_base is None else int(iq_base)
+        store_bytes = iq_dev.untyped_storage().nbytes() - iq_dev.storage_offset() * iq_dev.element_size()
+        code = iq_code(iq_dev)
+        L.check(L.load().sydr_trk_run_kaplan(iq_dev.data_ptr(), code, store_bytes // _IQ_BYTES[code], self.fs,
+                                             self._states.data_ptr(), self._kstates.data_ptr(), self.n_ch,
+                                             self._out.data_ptr(), self._kout.data_ptr(), self.max_epochs,
+                                             self._nep.data_ptr(), C.byref(self.cfg), _stream_ptr(stream)),
+                "sydr_trk_run_kaplan")
+
+    def kaplan_states(self) -> np.ndarray:
+        return self._kstates.cpu().numpy().view(L.KAPLAN_STATE_DTYPE).copy()
+
+    def fetch_kaplan(self):
+        """Per-channel arrays of the Kaplan extras (fll, cn0, lock indicators, lock state, flags), aligned
+        with the records of fetch()."""
+        nep = self._nep.cpu().numpy()
+        out = self._kout.cpu().numpy().view(L.KAPLAN_EPOCH_DTYPE).reshape(self.n_ch, self.max_epochs)
+        return [out[c, :nep[c]].copy() for c in range(self.n_ch)]

@@ -1,0 +1,99 @@
+"""Kaplan loop closure on the device (channel_l1ca_kaplan.py:342-619) against the live
+reference channel's packets (tests/golden/kaplan.npz) and, teacher-forced, against KaplanTrackOracle."""
+import numpy as np
+import pytest
+
+import helpers as H
+from oracle import sydr_oracle as O
+
+pytestmark = pytest.mark.gpu
+COLS = dict(corr=slice(1, 7), dll=7, pll=8, fll=9, carrier=10, code=11, cerr=12, derr=13, cn0=14, pll_lock=15, fll_lock=16,
+            state=17, flags=18, rem_code=19, rem_carrier=20, n_req=21)
+
+
+def _run(g, cluster=0, pieces=1):
+    from sydr_b200 import synth
+    from sydr_b200.engine import KaplanTrackingEngine, make_kaplan_states, to_device_iq
+    fs, nbits, seed, ms, ds = g["meta"]
+    prns = [int(p) for p in g["prns"]]
+    sc = synth.make_scenario(float(fs), int(nbits), int(ms) * 1e-3, tuple(prns), int(seed), float(ds))
+    iq = synth.generate_iq(sc)
+    assert H.sha(iq) == str(g["sha"])
+    n = len(iq) // 2
+    chans = []
+    for p in prns:
+        ra = g[f"acq_{p}"]                      # tick, freq_idx, code_idx, ratio, carrierFrequency, currentSample (ring index)
+        start = 10 * 4000 - 4001 + int(ra[2]) + 1                     # channel_l1ca_kaplan.py:223-240 from sample 0
+        chans.append(dict(prn=p, carrier_freq=float(ra[4]), start_sample=start, iq_len=n))
+    st, ks = make_kaplan_states(float(fs), chans, H.MG.KAPLAN_TRK_CFG)
+    eng = KaplanTrackingEngine(float(fs), st, ks, int(ms) + 8, cluster=cluster)
+    d = to_device_iq(iq)
+    if pieces == 1:
+        eng.launch(d)
+    else:
+        for k in range(1, pieces + 1):
+            eng.launch(d, iq_len=n * k // pieces, append=True)
+    return prns, iq, chans, eng.fetch(), eng.fetch_kaplan(), eng
+
+
+@pytest.mark.parametrize("cluster,pieces", [(0, 1), (2, 3), (1, 1)])
+def test_device_kaplan_follows_the_reference_channel(golden, cluster, pieces):
+    g = golden("kaplan.npz")
+    prns, iq, chans, recs, kex, eng = _run(g, cluster, pieces)
+    for c, p in enumerate(prns):
+        ref = g[f"trk_{p}"]
+        r, k = recs[c], kex[c]
+        n = min(len(r), len(ref))
+        assert n >= len(ref) - 2 and len(k) == len(r)
+        ref = ref[:n]
+        # loop outputs within the north star's tolerances
+        assert np.abs(r["carrier_freq"][:n] - ref[:, COLS["carrier"]]).max() <= 0.5
+        assert np.abs(r["code_freq"][:n] - ref[:, COLS["code"]]).max() <= 0.5
+        same = r["n"][1:n] == ref[:-1, COLS["n_req"]]                 # epoch lengths (n_req after epoch k = n of k+1)
+        assert same.mean() > 0.99
+        e = np.abs(r["corr"][:n] - ref[:, COLS["corr"]]).max(axis=1) / np.hypot(ref[:, 3], ref[:, 4])
+        assert np.median(e) <= 1e-3
+        # the state machine takes the same path (transitions may move by an epoch or two)
+        for st in (2, 3):
+            a, b = int(np.argmax(k["lock_state"][:n] == st)), int(np.argmax(ref[:, COLS["state"]] == st))
+            assert a > 0 and abs(a - b) <= 3, (p, st, a, b)
+        assert (int(k["flags"][n - 1]) & 3) == (int(ref[-1, COLS["flags"]]) & 3) == 3
+        assert abs(k["cn0"][n - 1] - ref[-1, COLS["cn0"]]) <= 0.05 * ref[-1, COLS["cn0"]]
+        assert np.abs(k["fll_lock"][:n] - ref[:, COLS["fll_lock"]]).max() <= 0.05
+        assert np.abs(k["pll_lock"][:n] - ref[:, COLS["pll_lock"]]).max() <= 0.05
+
+
+def test_device_kaplan_loop_math_teacher_forced(golden):
+    """Every epoch's loop update recomputed by the oracle from the device's own correlator sums and
+    previous state: the FP64 loop closure on the device equals the Python floats to rounding."""
+    g = golden("kaplan.npz")
+    prns, iq, chans, recs, kex, eng = _run(g)
+    x = iq[0::2] + 1j * iq[1::2]
+    for c, p in enumerate(prns):
+        o = O.KaplanTrackOracle(p, float(g["meta"][0]), chans[c]["carrier_freq"], chans[c]["start_sample"])
+        r, k = recs[c], kex[c]
+        for e in range(len(r)):
+            assert int(r["start"][e]) == o.cur and int(r["n"][e]) == o.n_req, (p, e)
+            if e % 97 == 0:                                            # open-loop correlator check on a subset
+                want = np.array(O.epl(x[o.cur:o.cur + o.n_req], o.code, o.fs, o.carrier_freq, o.rem_carrier, o.rem_code,
+                                      o.code_step, o.spacings))
+                assert np.abs(r["corr"][e] - want).max() <= 1e-4 * np.hypot(want[2], want[3]), (p, e)
+            w = o.step(None, corr_override=r["corr"][e])
+            tol = lambda a, b, rel=1e-9, ab=1e-12: abs(a - b) <= rel * abs(b) + ab
+            assert tol(r["carrier_freq"][e], w["carrier_frequency"]) and tol(r["code_freq"][e], w["code_frequency"]), (p, e)
+            assert tol(r["pll"][e], w["carrier_frequency_error"], 1e-7, 1e-10), (p, e)
+            assert tol(r["dll"][e], w["code_frequency_error"], 1e-7, 1e-10), (p, e)
+            assert tol(r["carrier_err"][e], w["pll"], 1e-9, 1e-13) and tol(k["fll"][e], w["fll"], 1e-7, 1e-9), (p, e)
+            assert tol(r["code_err"][e], w["dll"], 1e-9, 1e-13), (p, e)
+            assert tol(r["rem_carrier"][e], w["rem_carrier"], 1e-9, 1e-9) and tol(r["rem_code"][e], w["rem_code"], 1e-9, 1e-9)
+            assert tol(k["cn0"][e], w["cn0"]) and tol(k["fll_lock"][e], w["fll_lock"]) and tol(k["pll_lock"][e], w["pll_lock"])
+            assert int(k["lock_state"][e]) == w["lock_state"] and int(k["flags"][e]) == w["flags"], (p, e)
+            # keep the oracle on the device's trajectory (differences at rounding level would otherwise add up)
+            o.carrier_freq, o.code_freq = float(r["carrier_freq"][e]), float(r["code_freq"][e])
+            o.rem_carrier, o.rem_code = float(r["rem_carrier"][e]), float(r["rem_code"][e])
+            o.code_step = o.code_freq / o.fs
+            o.n_req = int(np.ceil((O.CODE_CHIPS - o.rem_code) / o.code_step))
+            o.vel_memory = o.vel_memory
+            o.cn0, o.fll_lock, o.pll_lock = float(k["cn0"][e]), float(k["fll_lock"][e]), float(k["pll_lock"][e])
+        ks = eng.kaplan_states()[c]
+        assert int(ks["code_counter"]) == len(r) and int(ks["lock_state"]) == 3
