@@ -331,6 +331,7 @@ def main():
     ap.add_argument("--threads", type=int, default=0)
     ap.add_argument("--no-tma", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-kaplan", action="store_true", help="skip the Kaplan loop-closure measurement")
     ap.add_argument("--stress-recordings", type=int, default=32, help="recordings of the cfg-5 throughput measurement (0 = skip)")
     ap.add_argument("--stress-seconds", type=float, default=0.5)
     ap.add_argument("--ingest-seconds", type=float, default=6.0, help="length of the file-ingest measurement (0 = skip)")
@@ -436,6 +437,31 @@ def main():
     ms_acq_alone = float(np.mean([m[0].elapsed_time(m[1]) for m in alone[1:]]))
     ms_trk_alone = float(np.mean([m[2].elapsed_time(m[3]) for m in alone[1:]]))
 
+    # ---- the Kaplan loop closure on the same chunk, one step in flight
+    kap = None
+    if world == 1 and not args.no_kaplan:
+        from sydr_b200.pipeline import ColdStartPipeline
+        kp = ColdStartPipeline(fs=FS, nbits=NBITS, search_prns=SEARCH_PRNS, n_channels=N_CHANNELS,
+                               max_seconds=args.chunk_seconds, device=dev, loop="kaplan", **ACQ)
+        ks = []
+        for _ in range(4):
+            m = []
+            kp.process_device(d_iq, m)
+            torch.cuda.synchronize()
+            ks.append(m[2].elapsed_time(m[3]))
+        ko = kp.finish(kp.enqueue_device(d_iq), records=True)
+        truth_k = {s.prn: s.doppler for s in sc.sats}
+        kerr = max(abs(float(np.mean(e["carrier_freq"][-200:])) - truth_k[c["prn"]]) for c, e in zip(ko["channels"], ko["epochs"]))
+        if kerr > 5.0:
+            raise SystemExit(f"Kaplan loops did not converge (|df| = {kerr:.1f} Hz)")
+        kms = float(np.mean(ks[1:]))
+        kap = {"kernel": "trk_borre_kernel (KAP instantiation: FLL-assisted PLL, lock detectors, lock-state machine)",
+               "alone_ms": kms, "alone_us_per_epoch": kms * 1e3 / (chunk_samples / (FS * 1e-3)),
+               "rtf_tracking": args.chunk_seconds * 1e3 / kms, "max_doppler_error_hz": kerr,
+               "lock_states_at_end": sorted(set(int(x["lock_state"][-1]) for x in ko["kaplan"]))}
+        kp.close()
+        del kp
+
     # ---- K steps end to end from pinned host memory
     run_steps(2, lambda m: pool.submit_host(host), True)
     barrier()
@@ -510,6 +536,8 @@ def main():
                     "kernels_note": f"ms = launch duration inside the timed region ({args.lanes} steps in flight: the "
                                     "acquisition of one step shares the GPU with the tracking of another); alone_ms = the "
                                     "same launch with one step in flight"}
+        if kap is not None:
+            roofline["kernels"]["kaplan_variant"] = kap
         if args.stress_recordings > 0 and world == 1:
             roofline["throughput_mode"] = throughput_stress(dev, args.stress_recordings, args.stress_seconds, tfv.value)
         line = {"metric": "cold acquisition (32 PRN) + 12-channel tracking throughput", "value": value, "unit": "Msamples/s",

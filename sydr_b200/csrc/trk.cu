@@ -1065,6 +1065,7 @@ struct KaplanRegs {                 // mutable members, registers of warp 1
     double ip_prev, qp_prev, fll_lock, pll_lock, cn0, pdpn, vel_memory, fll_bw, pll_bw;
     int accum_counter, lock_state, flags;
     long long code_counter;
+    double atan_prev;               // atan(qp_prev / ip_prev): the previous epoch's value of the one arctangent per epoch
 };
 __device__ __forceinline__ double np_sign(double x) { return (x > 0.0) ? 1.0 : ((x < 0.0) ? -1.0 : x); }   // 0 -> 0, nan -> nan
 
@@ -1080,13 +1081,15 @@ __device__ __forceinline__ double carrier_pre_kaplan(const SH& sh, const Carrier
     return rc;
 }
 
-__device__ __forceinline__ double fll_atan(double ip, double qp, double ipp, double qpp) {      // tracking.py:156-176
-    double e = atan(__ddiv_rn(qp, ip)) - atan(__ddiv_rn(qpp, ipp));
+// FLL_ATAN with the two arctangents handed in: atan(qp/ip) of this epoch also serves PLL_costa, and is the
+// next epoch's atan(qpPrev/ipPrev) (same operands, same value): one arctangent per epoch instead of three.
+__device__ __forceinline__ double fll_atan(double at_now, double at_prev) {                     // tracking.py:156-176
+    double e = at_now - at_prev;
     if (isnan(e)) e = 0.0;
     const double half_pi = kGpsPi / 2.0;
     if (e >= half_pi) e = dsub(e, kGpsPi);
     else if (e <= -half_pi) e = dadd(e, kGpsPi);
-    return __ddiv_rn(__ddiv_rn(e, 1e-3), kGpsPi * 2.0);
+    return ddiv(ddiv(e, 1e-3), kGpsPi * 2.0);
 }
 
 template <class SH>
@@ -1099,15 +1102,17 @@ __device__ __forceinline__ void carrier_close_kaplan(SH& sh, CarrierState& st, K
     if (k.accum_counter == 20) k.accum_counter = 0;
     k.accum_counter += 1;
     // runDiscriminators (L407-432)
+    const double at_now = atan(__ddiv_rn(qp, ip));
     double fll = 0.0, pll = 0.0;
     if (k.lock_state == 1) {
-        if (k.code_counter > 1) fll = fll_atan(ip, qp, k.ip_prev, k.qp_prev);
+        if (k.code_counter > 1) fll = fll_atan(at_now, k.atan_prev);
     } else {
-        fll = fll_atan(ip, qp, k.ip_prev, k.qp_prev);
-        pll = __ddiv_rn(atan(__ddiv_rn(qp, ip)), kGpsPi * 2.0);                          // PLL_costa
+        fll = fll_atan(at_now, k.atan_prev);
+        pll = ddiv(at_now, kGpsPi * 2.0);                                                // PLL_costa
     }
+    k.atan_prev = at_now;
     // FLLassistedPLL_2ndOrder (tracking.py:246-279), w0f = B_fll / 0.25, w0p = B_pll / 0.53
-    const double w0f = __ddiv_rn(k.fll_bw, 0.25), w0p = __ddiv_rn(k.pll_bw, 0.53);
+    const double w0f = dmul(k.fll_bw, 4.0), w0p = ddiv(k.pll_bw, 0.53);                   // x / 0.25 = 4 x exactly
     const double update = dmul(dadd(dmul(pll, dmul(w0p, w0p)), dmul(fll, w0f)), dmul(1.0, 1e-3));
     double cerr = dadd(update, k.vel_memory);
     k.vel_memory = update;
@@ -1117,12 +1122,12 @@ __device__ __forceinline__ void carrier_close_kaplan(SH& sh, CarrierState& st, K
         const double i2 = dmul(ip, ip), q2 = dmul(qp, qp);
         double lock = dsub(dmul(ip, k.ip_prev), dmul(qp, k.qp_prev));
         lock = dmul(lock, np_sign(dadd(dmul(ip, k.ip_prev), dmul(qp, k.qp_prev))));
-        lock = fabs(__ddiv_rn(lock, dadd(i2, q2)));
+        lock = fabs(ddiv(lock, dadd(i2, q2)));
         k.fll_lock = dadd(dmul(dsub(1.0, 0.005), k.fll_lock), dmul(0.005, lock));
         if (k.lock_state > 1)
-            k.pll_lock = dadd(dmul(dsub(1.0, 0.005), k.pll_lock), dmul(0.005, __ddiv_rn(dsub(i2, q2), dadd(i2, q2))));
+            k.pll_lock = dadd(dmul(dsub(1.0, 0.005), k.pll_lock), dmul(0.005, ddiv(dsub(i2, q2), dadd(i2, q2))));
         const double d = dsub(fabs(ip), fabs(qp));
-        k.pdpn = dadd(k.pdpn, __ddiv_rn(dadd(i2, q2), dmul(d, d)));
+        k.pdpn = dadd(k.pdpn, __ddiv_rn(dadd(i2, q2), dmul(d, d)));       // (|ip| - |qp|)^2 may be 0: IEEE division
         if (k.accum_counter == 20) {                                                     // CN0_Beaulieu, alpha = 0.1
             const double lam = __ddiv_rn(1.0, __ddiv_rn(k.pdpn, 20.0));
             const double neu = dmul(lam, __ddiv_rn(1.0, dmul(20.0, 1e-3)));
@@ -1274,6 +1279,7 @@ __global__ void __launch_bounds__(LEAN ? kLeanThreads : kTrkMaxThreads, LEAN ? 3
         kr.cn0 = g.cn0; kr.pdpn = g.pdpn; kr.vel_memory = g.vel_memory; kr.fll_bw = g.fll_bw; kr.pll_bw = g.pll_bw;
         kr.accum_counter = g.accum_counter; kr.lock_state = g.lock_state; kr.flags = g.flags;
         kr.code_counter = g.code_counter;
+        kr.atan_prev = atan(__ddiv_rn(g.qp_prev, g.ip_prev));
     }
     sydr_kaplan_epoch* kout_row = (KAP && rank == 0) ? P.kout + (long long)ch * P.max_epochs + sh.rec_base : nullptr;
     int status = sh.cfgs.status;                   // != 0: aborted earlier (< 0) or idle slot (> 0): no epochs

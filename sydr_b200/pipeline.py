@@ -15,8 +15,8 @@ import numpy as np
 import torch
 
 from . import _lib as L
-from .engine import (CODE_CHIPS, CODE_FREQ, IQ_PAD_BYTES, AcquisitionEngine, TrackingEngine, make_trk_states,
-                     n_complex_samples)
+from .engine import (CODE_CHIPS, CODE_FREQ, IQ_PAD_BYTES, AcquisitionEngine, KaplanTrackingEngine, TrackingEngine,
+                     make_kaplan_states, make_trk_states, n_complex_samples)
 
 
 def _mark():
@@ -28,7 +28,7 @@ def _mark():
 class ColdStartPipeline:
     def __init__(self, fs, nbits, search_prns, n_channels, doppler_range=5000.0, doppler_step=250.0, coh=1,
                  noncoh=10, max_seconds=2.0, inter_freq=0.0, threshold=1.5, channel_cfg=None, device=None,
-                 cluster=0, threads=0, use_tma=True):
+                 cluster=0, threads=0, use_tma=True, loop="borre"):
         L.require_device()
         if device is not None:
             torch.cuda.set_device(device)
@@ -49,11 +49,26 @@ class ColdStartPipeline:
         # Hand-off on the device (K-HAND): a template state with the loop coefficients, the tracking
         # engine for n_channels slots (unused ones idle) and a pinned landing zone for the peak table,
         # so that acquisition, hand-off and tracking are enqueued back to back with no host round trip.
-        tmpl = make_trk_states(self.fs, [dict(prn=1, carrier_freq=0.0, start_sample=0)], channel_cfg)
+        # loop = "borre" (channel_l1ca_borre.py, DLL + Costas PLL) or "kaplan" (channel_l1ca_kaplan.py, FLL-assisted
+        # PLL with lock detectors and the PULL_IN / WIDE / NARROW machine): which loop closure the kernel runs
+        self.loop = str(loop)
+        dummy = [dict(prn=1, carrier_freq=0.0, start_sample=0)]
+        if self.loop == "kaplan":
+            tmpl, ktmpl = make_kaplan_states(self.fs, dummy, channel_cfg)
+        elif self.loop == "borre":
+            tmpl, ktmpl = make_trk_states(self.fs, dummy, channel_cfg), None
+        else:
+            raise L.SydrError(f"unknown loop closure '{loop}'")
         self._tmpl = torch.from_numpy(tmpl.view(np.uint8).reshape(-1).copy()).to(self.device)
         idle = np.repeat(tmpl, self.n_channels)
         idle["status"] = 1
-        self._trk = TrackingEngine(self.fs, idle, self.max_epochs, device=self.device, **self.trk_cfg)
+        if ktmpl is None:
+            self._trk = TrackingEngine(self.fs, idle, self.max_epochs, device=self.device, **self.trk_cfg)
+            self._ktmpl = None
+        else:
+            ks = np.repeat(ktmpl, self.n_channels)
+            self._trk = KaplanTrackingEngine(self.fs, idle, ks, self.max_epochs, device=self.device, **self.trk_cfg)
+            self._ktmpl = self._trk._kstates.clone()          # fresh Kaplan states, copied in at every hand-off
         self._n_sel = torch.zeros(1, dtype=torch.int32, device=self.device)
         self._peaks_host = torch.empty(len(self.acq.prns) * 24, dtype=torch.uint8, pin_memory=True)
         self._track_required = int(math.ceil(CODE_CHIPS / (CODE_FREQ / self.fs)))
@@ -83,6 +98,8 @@ class ColdStartPipeline:
     def _handoff(self, n_samples: int, stream=None):
         """Enqueue K-HAND: peak table -> channel states on the device (channel_l1ca_borre.py:301-311)."""
         a = self.acq
+        if self._ktmpl is not None:
+            self._trk._kstates.copy_(self._ktmpl, non_blocking=True)
         L.check(L.load().sydr_acq_handoff(a.peaks_device().data_ptr(), len(a.prns), a.inter_freq, a.doppler_range,
                                           a.doppler_step, a.required_samples, self._track_required, 0,
                                           self.threshold, self._tmpl.data_ptr(), int(n_samples),
@@ -135,6 +152,8 @@ class ColdStartPipeline:
         out = dict(peaks=peaks, channels=chans)
         if records:
             out["epochs"] = self.collect(copy=copy)
+            if self._ktmpl is not None:
+                out["kaplan"] = self._trk.fetch_kaplan()[:self._n_active]
         return out
 
     def process_device(self, d_iq: torch.Tensor, marks: list | None = None) -> dict:

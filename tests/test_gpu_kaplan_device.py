@@ -97,3 +97,34 @@ def test_device_kaplan_loop_math_teacher_forced(golden):
             o.cn0, o.fll_lock, o.pll_lock = float(k["cn0"][e]), float(k["fll_lock"][e]), float(k["pll_lock"][e])
         ks = eng.kaplan_states()[c]
         assert int(ks["code_counter"]) == len(r) and int(ks["lock_state"]) == 3
+
+
+def test_pipeline_with_kaplan_loops_at_25_msps():
+    """ColdStartPipeline(loop="kaplan") at the headline rate (int16, 25 MS/s, clusters of 8): acquisition, device
+    hand-off, Kaplan tracking; every epoch's loop update teacher-forced against the oracle."""
+    from sydr_b200 import synth
+    from sydr_b200.engine import to_device_iq
+    from sydr_b200.pipeline import ColdStartPipeline
+    fs, prns = 25e6, (11, 27)
+    sc = synth.make_scenario(fs, 16, 0.35, prns, 55, 250.0)
+    iq = synth.generate_iq(sc)
+    pipe = ColdStartPipeline(fs, 16, list(range(1, 33)), 4, max_seconds=0.35, loop="kaplan")
+    out = pipe.finish(pipe.enqueue_device(to_device_iq(iq)), records=True, copy=True)
+    assert [c["prn"] for c in out["channels"]] == list(prns)
+    for ch, r, k in zip(out["channels"], out["epochs"], out["kaplan"]):
+        assert len(r) == len(k) >= 335
+        o = O.KaplanTrackOracle(ch["prn"], fs, ch["carrier_freq"], ch["start_sample"])
+        for e in range(len(r)):
+            assert int(r["start"][e]) == o.cur and int(r["n"][e]) == o.n_req
+            w = o.step(None, corr_override=r["corr"][e])
+            assert abs(r["carrier_freq"][e] - w["carrier_frequency"]) <= 1e-9 * abs(w["carrier_frequency"]) + 1e-10
+            assert abs(k["fll_lock"][e] - w["fll_lock"]) <= 1e-9 and abs(k["cn0"][e] - w["cn0"]) <= 1e-9 * abs(w["cn0"]) + 1e-12
+            assert int(k["lock_state"][e]) == w["lock_state"] and int(k["flags"][e]) == w["flags"]
+            o.carrier_freq, o.code_freq = float(r["carrier_freq"][e]), float(r["code_freq"][e])
+            o.rem_carrier, o.rem_code = float(r["rem_carrier"][e]), float(r["rem_code"][e])
+            o.code_step = o.code_freq / o.fs
+            o.n_req = int(np.ceil((O.CODE_CHIPS - o.rem_code) / o.code_step))
+            o.cn0, o.fll_lock, o.pll_lock = float(k["cn0"][e]), float(k["fll_lock"][e]), float(k["pll_lock"][e])
+        sat = [s for s in sc.sats if s.prn == ch["prn"]][0]
+        assert abs(float(np.mean(r["carrier_freq"][-100:])) - sat.doppler) < 5.0
+    pipe.close()
