@@ -9,11 +9,18 @@
 
 namespace sydr {
 
-__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
-__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+// Complex arithmetic on the packed FP32x2 pipe of sm_100 (FADD2 / FMUL2 / FFMA2: both components of a
+// complex number in one instruction, half the issue slots of the scalar forms).
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return __ffma2_rn(b, make_float2(-1.f, -1.f), a); }
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
-    return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+    // (a.x b.x - a.y b.y, a.x b.y + a.y b.x) = a.x * (b.x, b.y) + a.y * (-b.y, b.x)
+    const float2 t = __fmul2_rn(make_float2(a.y, a.y), make_float2(-b.y, b.x));
+    return __ffma2_rn(make_float2(a.x, a.x), b, t);
 }
+// s * a and a + s * b for a real scalar s
+__device__ __forceinline__ float2 cscale(float s, float2 a) { return __fmul2_rn(make_float2(s, s), a); }
+__device__ __forceinline__ float2 caxpy(float s, float2 b, float2 a) { return __ffma2_rn(make_float2(s, s), b, a); }
 // multiply by -j
 __device__ __forceinline__ float2 mul_mj(float2 a) { return make_float2(a.y, -a.x); }
 
@@ -39,8 +46,8 @@ template <> struct Dft<3> {
         const float s = 0.86602540378443864676f;
         const float2 t = cadd(u[1], u[2]);
         const float2 d = csub(u[1], u[2]);
-        const float2 m = make_float2(u[0].x - 0.5f * t.x, u[0].y - 0.5f * t.y);
-        const float2 n = mul_mj(make_float2(s * d.x, s * d.y));
+        const float2 m = caxpy(-0.5f, t, u[0]);
+        const float2 n = mul_mj(cscale(s, d));
         u[0] = cadd(u[0], t);
         u[1] = cadd(m, n);
         u[2] = csub(m, n);
@@ -62,11 +69,11 @@ template <> struct Dft<5> {
         const float s1 = 0.95105651629515357212f, s2 = 0.58778525229247312917f;
         const float2 t1 = cadd(u[1], u[4]), t2 = cadd(u[2], u[3]);
         const float2 t3 = csub(u[1], u[4]), t4 = csub(u[2], u[3]);
-        const float2 m1 = make_float2(u[0].x + c1 * t1.x + c2 * t2.x, u[0].y + c1 * t1.y + c2 * t2.y);
-        const float2 m2 = make_float2(u[0].x + c2 * t1.x + c1 * t2.x, u[0].y + c2 * t1.y + c1 * t2.y);
-        const float2 n1 = mul_mj(make_float2(s1 * t3.x + s2 * t4.x, s1 * t3.y + s2 * t4.y));
-        const float2 n2 = mul_mj(make_float2(s2 * t3.x - s1 * t4.x, s2 * t3.y - s1 * t4.y));
-        u[0] = make_float2(u[0].x + t1.x + t2.x, u[0].y + t1.y + t2.y);
+        const float2 m1 = caxpy(c2, t2, caxpy(c1, t1, u[0]));
+        const float2 m2 = caxpy(c1, t2, caxpy(c2, t1, u[0]));
+        const float2 n1 = mul_mj(caxpy(s2, t4, cscale(s1, t3)));
+        const float2 n2 = mul_mj(caxpy(-s1, t4, cscale(s2, t3)));
+        u[0] = cadd(cadd(u[0], t1), t2);
         u[1] = cadd(m1, n1);
         u[4] = csub(m1, n1);
         u[2] = cadd(m2, n2);
