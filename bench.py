@@ -322,8 +322,8 @@ def workload_config(args, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--chunk-seconds", type=float, default=2.0)
     ap.add_argument("--lanes", type=int, default=3, help="steps in flight per GPU (ColdStartPool)")
@@ -367,11 +367,23 @@ def main():
     torch.cuda.synchronize()
     gathered = torch.empty(world * len(SEARCH_PRNS) * 24, dtype=torch.uint8, device=dev) if world > 1 else None
 
+    comm = torch.cuda.Stream(device=dev) if world > 1 else None
+    gathered_l = [torch.empty_like(gathered) for _ in range(args.lanes)] if world > 1 else None
+    peaks_l = [torch.empty(len(SEARCH_PRNS) * 24, dtype=torch.uint8, device=dev) for _ in range(args.lanes)] if world > 1 else None
+
     def gather_peaks(ticket):                           # the acquisition peak table, 768 B per rank
         if world > 1:
+            # behind the acquisition (a snapshot of the peak table taken on the lane's side stream), on a
+            # communication stream of its own: a slow peer delays neither this rank's tracking nor its host
             lane = pool.lane_index(ticket)
-            with torch.cuda.stream(pool.peak_stream(lane)):          # behind the acquisition, beside the tracking
-                dist.all_gather_into_tensor(gathered, pool.lanes[lane].acq.peaks_device())
+            side = pool.peak_stream(lane)
+            with torch.cuda.stream(side):
+                peaks_l[lane].copy_(pool.lanes[lane].acq.peaks_device(), non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(side)
+            comm.wait_event(ev)
+            with torch.cuda.stream(comm):
+                dist.all_gather_into_tensor(gathered_l[lane], peaks_l[lane])
 
     def run_steps(n, submit, records, marks_out=None):
         """n steps with at most `lanes` in flight; results collected in order."""
