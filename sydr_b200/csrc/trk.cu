@@ -20,6 +20,8 @@
 // sums are all-gathered with st.async (DSMEM store + remote mbarrier complete_tx), after which
 // every CTA closes the loops redundantly in FP64 (bit-identical), so one exchange per epoch
 // is the only inter-CTA synchronisation.
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace sydr {
@@ -885,12 +887,12 @@ struct TrkSharedT {          // static shared memory of the closed-loop kernel
     int n_hist[2];           // samples of epoch e (index e & 1), for the carrier warp
     int rec_base;            // index of this call's first record in the channel's output row
     int status;
-    sydr_kaplan_state kcfg;  // Kaplan loop closure: the channel's configuration and state as loaded / to store
     int seg_ok;              // segment path usable for this channel (spacings on the half-chip lattice)
     int seg_q[3];            // tap offsets in half chips
     uint32_t segtab[NTAB];   // sign bytes of the three taps per lattice index
     long long pc[16];        // diagnostics
     long long tprev, tprev1;
+    sydr_kaplan_state kcfg;  // Kaplan loop closure: the channel's configuration and state as loaded / to store
 };
 
 // TMA bulk copy of one CTA's window of the epoch starting at sample `a` (executed by one lane).
@@ -1231,7 +1233,7 @@ __global__ void __launch_bounds__(LEAN ? kLeanThreads : kTrkMaxThreads, LEAN ? 3
         sh.K.dll_c1 = g.dll_tau2 / g.dll_tau1; sh.K.dll_c2 = g.dll_pdi / g.dll_tau1;
         sh.K.pll_c1 = g.pll_tau2 / g.pll_tau1; sh.K.pll_c2 = g.pll_pdi / g.pll_tau1;
         sh.status = sh.cfgs.status;
-        if (KAP) sh.kcfg = P.kstates[ch];
+        if constexpr (KAP) sh.kcfg = P.kstates[ch];
         sh.seg_ok = (NV > 0 && P.seg) ? (seg_tap_offsets(sh.cfgs.spacing, sh.seg_q) ? 1 : 0) : 0;
         for (int k = 0; k < 16; ++k) sh.pc[k] = 0;
         mbar_init(&sh.bar_data[0], 1);
@@ -1272,8 +1274,9 @@ __global__ void __launch_bounds__(LEAN ? kLeanThreads : kTrkMaxThreads, LEAN ? 3
     // loop state lives in registers of its owning warp (warp 0: code, warp 1: carrier)
     CodeState sc = sh.sc;
     CarrierState sk = sh.sk;
-    KaplanRegs kr = {};
-    if (KAP) {
+    struct NoKaplan {};
+    typename std::conditional<KAP, KaplanRegs, NoKaplan>::type kr = {};
+    if constexpr (KAP) {
         const sydr_kaplan_state& g = sh.kcfg;
         kr.ip_prev = g.ip_prev; kr.qp_prev = g.qp_prev; kr.fll_lock = g.fll_lock; kr.pll_lock = g.pll_lock;
         kr.cn0 = g.cn0; kr.pdpn = g.pdpn; kr.vel_memory = g.vel_memory; kr.fll_bw = g.fll_bw; kr.pll_bw = g.pll_bw;
@@ -1281,7 +1284,8 @@ __global__ void __launch_bounds__(LEAN ? kLeanThreads : kTrkMaxThreads, LEAN ? 3
         kr.code_counter = g.code_counter;
         kr.atan_prev = atan(__ddiv_rn(g.qp_prev, g.ip_prev));
     }
-    sydr_kaplan_epoch* kout_row = (KAP && rank == 0) ? P.kout + (long long)ch * P.max_epochs + sh.rec_base : nullptr;
+    sydr_kaplan_epoch* kout_row = nullptr;
+    if constexpr (KAP) kout_row = (rank == 0) ? P.kout + (long long)ch * P.max_epochs + sh.rec_base : nullptr;
     int status = sh.cfgs.status;                   // != 0: aborted earlier (< 0) or idle slot (> 0): no epochs
     int epoch = 0;
     // loop-invariant limits of the stop test
@@ -1462,7 +1466,8 @@ __global__ void __launch_bounds__(LEAN ? kLeanThreads : kTrkMaxThreads, LEAN ? 3
             CodePre cpre = {0.0, 0.0};
             double rc_next = 0.0;
             if (warp == 0) cpre = code_pre(sc);
-            else rc_next = KAP ? carrier_pre_kaplan(sh, sk, sh.n_hist[e & 1]) : carrier_pre(sh, sk, sh.n_hist[e & 1]);
+            else if constexpr (KAP) rc_next = carrier_pre_kaplan(sh, sk, sh.n_hist[e & 1]);
+            else rc_next = carrier_pre(sh, sk, sh.n_hist[e & 1]);
             mbar_wait(&sh.bar_gather[slot], (e >> 1) & 1);       // st.async data is visible once the phase completes
             SYDR_TICK(5)                               // all-gather: wait for the slowest warp of the cluster
             SYDR_TICK1(10)                             // carrier warp: everything up to the gather
@@ -1470,9 +1475,12 @@ __global__ void __launch_bounds__(LEAN ? kLeanThreads : kTrkMaxThreads, LEAN ? 3
             SYDR_TICK(7)                               // totals
             SYDR_TICK1(11)
             sydr_trk_epoch* rec = out_row ? out_row + e : nullptr;
-            if (warp == 0) code_close(sh, sc, status, ck, rec, lane, cpre);
-            else if (KAP) carrier_close_kaplan(sh, sk, kr, ck, rc_next, rec, kout_row ? kout_row + e : nullptr, lane);
-            else carrier_close(sh, sk, ck, rc_next, rec, lane);
+            if (warp == 0) {
+                code_close(sh, sc, status, ck, rec, lane, cpre);
+            } else {
+                if constexpr (KAP) carrier_close_kaplan(sh, sk, kr, ck, rc_next, rec, kout_row ? kout_row + e : nullptr, lane);
+                else carrier_close(sh, sk, ck, rc_next, rec, lane);
+            }
             SYDR_TICK(6)                               // loop closure
             SYDR_TICK1(12)
         }
@@ -1483,7 +1491,7 @@ __global__ void __launch_bounds__(LEAN ? kLeanThreads : kTrkMaxThreads, LEAN ? 3
 
     if (warp == 0 && lane == 0) sh.sc = sc;
     if (warp == 1 && lane == 0) sh.sk = sk;
-    if (KAP && warp == 1 && lane == 0) {
+    if constexpr (KAP) if (warp == 1 && lane == 0) {
         sydr_kaplan_state& g = sh.kcfg;
         g.ip_prev = kr.ip_prev; g.qp_prev = kr.qp_prev; g.fll_lock = kr.fll_lock; g.pll_lock = kr.pll_lock;
         g.cn0 = kr.cn0; g.pdpn = kr.pdpn; g.vel_memory = kr.vel_memory; g.fll_bw = kr.fll_bw; g.pll_bw = kr.pll_bw;
@@ -1502,7 +1510,7 @@ __global__ void __launch_bounds__(LEAN ? kLeanThreads : kTrkMaxThreads, LEAN ? 3
         gst->nco_code = sh.sc.nco_code; gst->nco_code_err = sh.sc.nco_code_err;
         gst->nco_carrier = sh.sk.nco_carrier; gst->nco_carrier_err = sh.sk.nco_carrier_err;
         gst->status = sh.status;
-        if (KAP) P.kstates[ch] = sh.kcfg;
+        if constexpr (KAP) P.kstates[ch] = sh.kcfg;
         P.nepochs[ch] = sh.rec_base + epoch;
     }
     if (S > 1) cluster_sync_all();                  // nobody leaves while peers may still write here
