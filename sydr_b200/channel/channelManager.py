@@ -186,11 +186,22 @@ class ChannelManager:
         """channelManager.py:149-188: process the current buffer content, return the flattened
         packets of all channels for this millisecond."""
         active = [c for c in self.channels.values() if c.is_alive()]
-        self._acquire([c for c in active if c.channelState is ChannelState.ACQUIRING])
-        tracking = [c for c in active if c.channelState is ChannelState.TRACKING]
+        # Channel classes without a device loop closure in this dispatcher (the Kaplan variant) run their own
+        # _processHandler() per tick, like the reference's channel process: GPU correlators / acquisition through
+        # the drop-in functions, loops on the host.  They read the host copy of the ring.
+        alone = [c for c in active if not hasattr(c, "_trackingConfiguration")]
+        if alone and self.sharedBuffer.buffer is None:
+            raise L.SydrError("channels ticked stand-alone need ChannelManager(hostCopy=True)")
+        batched = [c for c in active if hasattr(c, "_trackingConfiguration")]
+        self._acquire([c for c in batched if c.channelState is ChannelState.ACQUIRING])
+        tracking = [c for c in batched if c.channelState is ChannelState.TRACKING]
         self._track_ahead(tracking)
         results = []
         for chan in active:
+            if chan in alone:
+                results.extend(chan._processHandler())
+                results.append(chan.prepareChannelUpdate())
+                continue
             packets = []
             acq = getattr(chan, "_pendingAcquisition", None)
             if acq is not None:

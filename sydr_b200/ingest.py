@@ -28,7 +28,8 @@ import numpy as np
 import torch
 
 from . import _lib as L
-from .engine import IQ_PAD_BYTES, AcquisitionEngine, NavBitEngine, TrackingEngine, make_trk_states
+from .engine import (IQ_PAD_BYTES, AcquisitionEngine, KaplanTrackingEngine, NavBitEngine, TrackingEngine,
+                     make_kaplan_states, make_trk_states)
 
 
 class FileChunkReader:
@@ -130,7 +131,7 @@ class StreamingReceiver:
 
     def __init__(self, rf, search_prns, n_channels, chunk_seconds=1.0, doppler_range=5000.0, doppler_step=250.0,
                  coh=1, noncoh=10, threshold=1.5, channel_cfg=None, want_records=True, want_bits=True,
-                 reader_threads=8, device=None, cluster=0, threads=0, use_tma=True):
+                 reader_threads=8, device=None, cluster=0, threads=0, use_tma=True, loop="borre"):
         L.require_device()
         if not rf.isComplex:
             raise L.SydrError("StreamingReceiver needs interleaved I,Q samples (is_complex = true)")
@@ -143,7 +144,10 @@ class StreamingReceiver:
         self.nbits = 8 * self.np_dtype.itemsize
         self._tdt = torch.int8 if self.nbits == 8 else torch.int16
         self.n_channels, self.threshold, self.channel_cfg = int(n_channels), float(threshold), channel_cfg
-        self.want_records, self.want_bits = bool(want_records), bool(want_bits)
+        self.loop = str(loop)                  # "borre" or "kaplan": which loop closure the tracking kernel runs
+        if self.loop not in ("borre", "kaplan"):
+            raise L.SydrError(f"unknown loop closure '{loop}'")
+        self.want_records, self.want_bits = bool(want_records), bool(want_bits and self.loop == "borre")
         self.reader_threads = int(reader_threads)
         self.trk_cfg = dict(cluster=cluster, threads=threads, use_tma=use_tma)
         self.acq = AcquisitionEngine(self.fs, float(rf.interFrequency), doppler_range, doppler_step, coh, noncoh,
@@ -180,8 +184,17 @@ class StreamingReceiver:
             carrier, _, cur = self.acq.handoff(peaks[i])
             chans.append(dict(prn=int(peaks["prn"][i]), carrier_freq=carrier, start_sample=cur, iq_len=0))
         if chans:
-            states = make_trk_states(self.fs, chans, self.channel_cfg)
             n_ch = len(chans)
+            if self.loop == "kaplan":
+                states, kstates = make_kaplan_states(self.fs, chans, self.channel_cfg)
+                self._trk = KaplanTrackingEngine(self.fs, states, kstates, self.max_epochs, device=self.device,
+                                                 **self.trk_cfg)
+                self._rec_host = [torch.empty(n_ch * self.max_epochs * 128, dtype=torch.uint8, pin_memory=True)
+                                  for _ in range(2)]
+                self._krec_host = [torch.empty(n_ch * self.max_epochs * 40, dtype=torch.uint8, pin_memory=True)
+                                   for _ in range(2)]
+                return chans
+            states = make_trk_states(self.fs, chans, self.channel_cfg)
             if self._trk is not None and self._trk.n_ch == n_ch:        # a receiver that is run again keeps its buffers
                 self._trk.reset(states)
                 if self._nav is not None:
@@ -206,6 +219,9 @@ class StreamingReceiver:
         if self.want_records:
             rec = self._rec_host[k & 1].numpy().view(L.TRK_EPOCH_DTYPE).reshape(n_ch, self.max_epochs)
             out["epochs"] = [rec[c, :nep[c]].copy() for c in range(n_ch)]
+            if self.loop == "kaplan":
+                kr = self._krec_host[k & 1].numpy().view(L.KAPLAN_EPOCH_DTYPE).reshape(n_ch, self.max_epochs)
+                out["kaplan"] = [kr[c, :nep[c]].copy() for c in range(n_ch)]
         if self.want_bits:
             out["bits"] = self._unpack_bits(self._bits_pending.pop(k), n_ch)
         return out
@@ -253,6 +269,8 @@ class StreamingReceiver:
                         self._bits_pending[k] = (self._nav._nbits.clone(), self._nav._bits.clone())
                     if self.want_records:
                         self._rec_host[k & 1].copy_(self._trk._out, non_blocking=True)
+                        if self.loop == "kaplan":
+                            self._krec_host[k & 1].copy_(self._trk._kout, non_blocking=True)
                 done.record(comp)
                 win_free[k & 1] = done
                 # ---- results of the previous chunk while this one runs
@@ -299,10 +317,16 @@ class StreamingReceiver:
             if "bits" in res:
                 for c, b in enumerate(res["bits"]):
                     bits[c].append(b)
+            if "kaplan" in res:
+                kap = out.setdefault("_kap", [[] for _ in res["kaplan"]])
+                for c, kx in enumerate(res["kaplan"]):
+                    kap[c].append(kx)
         if ep is not None and self.want_records:
             out["epochs"] = [np.concatenate(e) if e else np.zeros(0, dtype=L.TRK_EPOCH_DTYPE) for e in ep]
         if bits is not None and self.want_bits:
             out["bits"] = [np.concatenate(b) if b else np.zeros(0, dtype=np.int8) for b in bits]
+        if "_kap" in out:
+            out["kaplan"] = [np.concatenate(kx) for kx in out.pop("_kap")]
         if self._trk is not None:
             out["states"] = self._trk.states()
         return out
@@ -356,7 +380,8 @@ class StreamingReceiver:
                 s = int(sync[k])
                 # a synchronisation found later than this chunk does not reach back into it
                 cn0 = cn0_column(done[k], len(rec), s if 0 <= s < done[k] + len(rec) else -1)
-                database.addTrackingRecords(cid, rec, time=float(now()), time_sample=tick, cn0=cn0)
+                database.addTrackingRecords(cid, rec, time=float(now()), time_sample=tick, cn0=cn0,
+                                            kaplan=res["kaplan"][k] if "kaplan" in res else None)
                 done[k] += len(rec)
                 rows += len(rec)
             database.commit()

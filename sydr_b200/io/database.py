@@ -33,6 +33,11 @@ TRACKING_KEYS = ("cid", "i_early", "q_early", "i_prompt", "q_prompt", "i_late", 
                  "carrier_frequency", "code_frequency", "cn0", "pll_lock", "fll_lock", "lock_state",
                  "carrier_frequency_error", "code_frequency_error", "channel_id", "time", "time_sample")
 
+# The Kaplan channel's TRACKING_UPDATE keys in its own order (channel_l1ca_kaplan.py:657-681).
+KAPLAN_TRACKING_KEYS = ("cid", "i_early", "q_early", "i_prompt", "q_prompt", "i_late", "q_late", "carrier_frequency",
+                        "code_frequency", "carrier_frequency_error", "code_frequency_error", "cn0", "pll_lock", "fll_lock",
+                        "dll", "pll", "fll", "lock_state", "channel_id", "time", "time_sample")
+
 _TABLES = {
     "channel": ("""CREATE TABLE IF NOT EXISTS channel (
                         id INTEGER PRIMARY KEY,
@@ -190,7 +195,7 @@ class DatabaseHandler:
 
     # ---- columnar fast path ----------------------------------------------------------------
     def addTrackingRecords(self, cid: int, records: np.ndarray, time, time_sample, cn0=None, channel_id=None,
-                           fll: float = 0.0):
+                           fll: float = 0.0, kaplan: np.ndarray | None = None):
         """Insert the TRACKING_UPDATE rows of one channel straight from the device's per-epoch
         records (`sydr_trk_epoch` array): the same rows, in the same column order, that
         `addData("tracking", packet)` + `commit()` produce from ChannelL1CA.runTracking's packets
@@ -201,6 +206,8 @@ class DatabaseHandler:
             return
         if self.dictBuffer.get("tracking"):
             self.commit()                                       # keep arrival order
+        if kaplan is not None:
+            return self._addKaplanRecords(cid, records, kaplan, time, time_sample, channel_id)
         self._ensure_columns("tracking", TRACKING_KEYS, {"cid": "INTEGER", "lock_state": "INTEGER",
                                                          "channel_id": "INTEGER", "time_sample": "INTEGER"})
         corr = records["corr"]
@@ -218,6 +225,29 @@ class DatabaseHandler:
             records["carrier_err"].tolist(), records["code_err"].tolist(),
             [int(cid if channel_id is None else channel_id)] * n, col(time), col(time_sample, int)]
         self._insert("tracking", TRACKING_KEYS, zip(*cols))
+
+    def _addKaplanRecords(self, cid, records, kaplan, time, time_sample, channel_id):
+        """Rows of the Kaplan channel's packets (channel_l1ca_kaplan.py:657-681) from the device records and
+        their Kaplan extras: `dll` / `pll` / `fll` are the discriminators, `carrier_frequency_error` /
+        `code_frequency_error` the loop-filter outputs, `lock_state` the LoopLockState value."""
+        n = len(records)
+        assert len(kaplan) == n
+        self._ensure_columns("tracking", KAPLAN_TRACKING_KEYS, {"cid": "INTEGER", "lock_state": "INTEGER",
+                                                                "channel_id": "INTEGER", "time_sample": "INTEGER"})
+        corr = records["corr"]
+
+        def col(x, conv=float):
+            if np.ndim(x) == 0:
+                return [conv(x)] * n
+            return np.asarray(x).tolist() if conv is float else [int(v) for v in x]
+
+        cols = [[int(cid)] * n] + [corr[:, k].tolist() for k in range(6)] + [
+            records["carrier_freq"].tolist(), records["code_freq"].tolist(), records["pll"].tolist(),
+            records["dll"].tolist(), kaplan["cn0"].tolist(), kaplan["pll_lock"].tolist(), kaplan["fll_lock"].tolist(),
+            records["code_err"].tolist(), records["carrier_err"].tolist(), kaplan["fll"].tolist(),
+            [int(v) for v in kaplan["lock_state"]],
+            [int(cid if channel_id is None else channel_id)] * n, col(time), col(time_sample, int)]
+        self._insert("tracking", KAPLAN_TRACKING_KEYS, zip(*cols))
 
     def _ensure_columns(self, table, keys, int_keys):
         for key in keys:

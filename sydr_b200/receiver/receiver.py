@@ -33,8 +33,9 @@ class ReceiverState:
 
 
 class Receiver:
-    def __init__(self, configuration, overwrite=True, gui=None):
-        """receiver.py:58-97."""
+    def __init__(self, configuration, overwrite=True, gui=None, hostCopy=False):
+        """receiver.py:58-97.  hostCopy: keep a host copy of the 100 ms ring (channel classes that are ticked
+        stand-alone read it)."""
         self.configuration = configuration
         self.name = str(configuration['DEFAULT']['name'])
         self.msToProcess = int(configuration['DEFAULT']['ms_to_process'])
@@ -45,7 +46,7 @@ class Receiver:
         self.measurementFrequency = (float(configuration['MEASUREMENTS']['frequency'])
                                      if 'MEASUREMENTS' in configuration else 1.0)
         self.receiverState = ReceiverState.IDLE
-        self.channelManager = ChannelManager(self.rfSignal, keepCorrelationMaps=False)
+        self.channelManager = ChannelManager(self.rfSignal, keepCorrelationMaps=False, hostCopy=hostCopy)
         self.samplesCounter = 0
         self.channelsStatus = {}
         self.satelliteDict = {}

@@ -16,13 +16,13 @@ from .receiver import Receiver
 
 class ReceiverGPSL1CA(Receiver):
     def __init__(self, configuration, overwrite=True, gui=None):
-        super().__init__(configuration, overwrite, gui)
-        self.prnList = list(map(int, self.configuration.get('SATELLITES', 'include_prn').split(',')))
         channelConfig = configparser.ConfigParser()
-        if not channelConfig.read(self.configuration['CHANNELS']['gps_l1ca']):
-            raise FileNotFoundError(self.configuration['CHANNELS']['gps_l1ca'])
-        self.channelConfig = channelConfig
+        if not channelConfig.read(configuration['CHANNELS']['gps_l1ca']):
+            raise FileNotFoundError(configuration['CHANNELS']['gps_l1ca'])
         kaplan = 'fll_bandwidth_pullin' in channelConfig['TRACKING']
+        super().__init__(configuration, overwrite, gui, hostCopy=kaplan)
+        self.prnList = list(map(int, self.configuration.get('SATELLITES', 'include_prn').split(',')))
+        self.channelConfig = channelConfig
         self.channelClass = ChannelL1CA_Kaplan if kaplan else ChannelL1CA
         self.channelManager.addChannel(self.channelClass, channelConfig, len(self.prnList))
         for prn in self.prnList:
@@ -50,17 +50,16 @@ class ReceiverGPSL1CA(Receiver):
                 raise ValueError(f"Unknown channel message '{packet['type']}' received from channel {packet['cid']}.")
 
     def run_fast(self, chunk_seconds: float = 1.0):
-        """Whole-file processing of the Borre configuration through the streaming path: the PRNs of
+        """Whole-file processing through the streaming path (Borre or Kaplan loop closure on the device): the PRNs of
         [SATELLITES] are searched in the first chunk, the ones found tracked to the end of the file (or
         ms_to_process), rows inserted column-wise.  Same database tables as run()."""
         from ..ingest import StreamingReceiver
-        if self.channelClass is not ChannelL1CA:
-            raise NotImplementedError("run_fast() drives the Borre loop closure (device kernel); use run() for Kaplan")
         acq, trk = self.channelConfig['ACQUISITION'], dict(self.channelConfig['TRACKING'])
         rx = StreamingReceiver(self.rfSignal, self.prnList, len(self.prnList), chunk_seconds=chunk_seconds,
                                doppler_range=float(acq['doppler_range']), doppler_step=float(acq['doppler_steps']),
                                coh=int(acq['coherent_integration']), noncoh=int(acq['non_coherent_integration']),
-                               threshold=float(acq['threshold']), channel_cfg=trk)
+                               threshold=float(acq['threshold']), channel_cfg=trk,
+                               loop="kaplan" if self.channelClass is ChannelL1CA_Kaplan else "borre")
         try:
             ids = {int(ch.satelliteID): cid for cid, ch in self.channelManager.channels.items()}
             self.database.commit()                                  # the channel rows registered at construction

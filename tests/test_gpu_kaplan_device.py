@@ -128,3 +128,49 @@ def test_pipeline_with_kaplan_loops_at_25_msps():
         sat = [s for s in sc.sats if s.prn == ch["prn"]][0]
         assert abs(float(np.mean(r["carrier_freq"][-100:])) - sat.doppler) < 5.0
     pipe.close()
+
+
+def test_receiver_with_the_kaplan_ini(tmp_path):
+    """ReceiverGPSL1CA picks the Kaplan channel from the channel ini: run() ticks the host class over the GPU
+    correlators, run_fast() runs the loop closure on the device; both write Kaplan tracking rows that agree
+    within the north star's tolerances, with the same lock-state path."""
+    import configparser
+    import os
+    from sydr_b200 import synth
+    from sydr_b200.receiver.receiver_gps_l1ca import ReceiverGPSL1CA
+    fs, nbits, ms = 4e6, 8, 700
+    sc = synth.make_scenario(fs, nbits, ms * 1e-3 + 0.13, (3, 19), 31, 250.0)
+    path = str(tmp_path / "rec.bin")
+    synth.write_file(path, synth.generate_iq(sc))
+
+    def config(name):
+        cfg = configparser.ConfigParser()
+        cfg.read(os.path.join(H.ROOT, "config", "receiver.ini"))
+        cfg["DEFAULT"].update({"name": name, "ms_to_process": str(ms), "outfolder": str(tmp_path)})
+        cfg["RFSIGNAL"].update({"filepath": path, "sampling_frequency": str(fs), "data_size": str(nbits)})
+        cfg["SATELLITES"]["include_prn"] = "3,19"
+        cfg["CHANNELS"]["gps_l1ca"] = os.path.join(H.ROOT, "config", "channels", "channel_GPS_L1CA_kaplan.ini")
+        return cfg
+
+    b = ReceiverGPSL1CA(config("fast"), overwrite=True)
+    assert b.channelClass.__name__ == "ChannelL1CA_Kaplan"
+    b.run_fast(chunk_seconds=0.2)
+    rows_b = {c: b.database.fetchTracking(c) for c in (0, 1)}
+    b.close()
+    a = ReceiverGPSL1CA(config("tick"), overwrite=True)
+    a.run()
+    rows_a = {c: a.database.fetchTracking(c) for c in (0, 1)}
+    a.close()
+    for c in (0, 1):
+        ra, rb = rows_a[c], rows_b[c]
+        n = min(len(ra), len(rb))
+        assert n >= ms - 15
+        cf = lambda rows, k: np.array([r[k] for r in rows[:n]], dtype=np.float64)
+        assert np.abs(cf(ra, "carrier_frequency") - cf(rb, "carrier_frequency")).max() <= 0.5
+        assert np.abs(cf(ra, "code_frequency") - cf(rb, "code_frequency")).max() <= 0.5
+        assert np.abs(cf(ra, "fll_lock") - cf(rb, "fll_lock")).max() <= 0.05
+        sa, sb = cf(ra, "lock_state"), cf(rb, "lock_state")
+        assert set(sa.astype(int)) == set(sb.astype(int)) and 2 in set(sb.astype(int))
+        for st in sorted(set(sb.astype(int)) - {1}):
+            assert abs(int(np.argmax(sa == st)) - int(np.argmax(sb == st))) <= 3
+        assert set(ra[0]) == set(rb[0])                                   # same columns
