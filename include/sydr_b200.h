@@ -172,7 +172,7 @@ typedef struct {
 } sydr_trk_epoch;           /* 128 bytes */
 
 /* Launch configuration of the closed-loop kernel.  cluster = CTAs cooperating on one
- * channel (1,2,4,8); threads = threads per CTA (multiple of 32, <= 1024).  0 = auto. */
+ * channel (1,2,4,8); threads = threads per CTA (multiple of 32, 64..384).  0 = auto. */
 typedef struct {
     int32_t cluster;
     int32_t threads;

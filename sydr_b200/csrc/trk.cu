@@ -865,8 +865,9 @@ struct EpochCtl {            // published by warps 0 / 1 for every epoch
 
 constexpr int kMaxCluster = 8;
 constexpr int kWinTail = 32;     // samples staged beyond a CTA's window (segments that start inside may end outside)
-constexpr int kTrkMaxThreads = 640;
+constexpr int kTrkMaxThreads = 384;
 constexpr int kLeanThreads = 256;
+constexpr int kKaplanMaxThreads = 384;   // the Kaplan carrier warp holds more state: 170 registers per thread instead of 102
 constexpr int kNeedGeneral = 2;  // channel status: stopped in front of an epoch only the general kernel serves
 
 constexpr int kTrkMaxWarps = kTrkMaxThreads / 32;
@@ -1195,7 +1196,8 @@ __device__ __forceinline__ void carrier_close_kaplan(SH& sh, CarrierState& st, K
 // KAP = the carrier warp closes the Kaplan loops (FLL-assisted PLL, lock indicators, C/N0, lock-state
 // machine) instead of the Borre PLL; the code loop and everything else are shared.
 template <int DT, int VPC, bool TMA, bool LEAN, bool PROF = false, bool KAP = false>
-__global__ void __launch_bounds__(LEAN ? kLeanThreads : kTrkMaxThreads, LEAN ? 3 : 1) trk_borre_kernel(const TrkParams P) {
+__global__ void __launch_bounds__(LEAN ? kLeanThreads : (KAP ? kKaplanMaxThreads : kTrkMaxThreads), LEAN ? 3 : 1)
+trk_borre_kernel(const TrkParams P) {
     constexpr int SPV = IqTraits<DT>::SPV, BPS = IqTraits<DT>::BPS;
     constexpr int C = SPV * VPC;
     extern __shared__ __align__(128) uint8_t dyn_smem[];
@@ -1715,6 +1717,7 @@ static int trk_run_impl(const void* d_iq, int iq_dtype, long long iq_alloc_sampl
         threads = (((want + rounds - 1) / rounds) + 31) / 32 * 32;
         if (threads < 64) threads = 64;                    // warps 0 and 1 close the two loops
     }
+    if (d_kstates != nullptr && threads > kKaplanMaxThreads) threads = kKaplanMaxThreads;
     SYDR_REQUIRE(threads % 32 == 0 && threads >= 64 && threads <= kTrkMaxThreads, SYDR_ERR_ARG, "threads must be a multiple of 32 in [64, %d] (got %d)", kTrkMaxThreads, threads);
 
     // Throughput instantiation (LEAN): int16 IQ whose half chip fits the segment path, one CTA of

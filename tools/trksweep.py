@@ -14,7 +14,7 @@ acq = AcquisitionEngine(fs, 0.0, 5000, 250, 1, 10, list(synth.PRNS_12))
 peaks = acq.run(d_all)["peaks"]
 chans = [dict(prn=int(p["prn"]), carrier_freq=acq.handoff(p)[0], start_sample=acq.handoff(p)[2], iq_len=d_all.numel() // 2) for p in peaks]
 L.load().sydr_trk_profile_buffer(None)
-for cluster, threads in ((8, 0), (8, 256), (8, 224), (8, 192), (8, 160), (8, 128), (8, 96), (8, 544), (4, 0), (4, 288), (4, 416), (2, 0), (1, 0), (1, 352)):
+for cluster, threads in ((8, 0), (8, 256), (8, 224), (8, 192), (8, 160), (8, 128), (8, 96), (4, 0), (4, 288), (2, 0), (1, 0), (1, 352)):
     ts = []
     for rep in range(3):
         eng = TrackingEngine(fs, make_trk_states(fs, chans), 1100, cluster=cluster, threads=threads)
