@@ -26,6 +26,7 @@ from ..utils.constants import (GPS_L1CA_CODE_FREQ, GPS_L1CA_CODE_MS, GPS_L1CA_CO
                                LNAV_SUBFRAME_SIZE, LNAV_WORD_SIZE)
 from ..utils.enumerations import ChannelMessage, ChannelState, GNSSSignalType, GNSSSystems, TrackingFlags
 from .channel import Channel, ChannelStatus
+from .lnav_frame import advance_frame
 
 
 class ChannelL1CA(Channel):
@@ -259,37 +260,10 @@ class ChannelL1CA(Channel):
         self.navBitsCounter += 1
         self.navPromptSum = 0.0
         self.navPromptSumCounter = 0
-        minBits = 2 + 2 * LNAV_WORD_SIZE
-        if self.navBitsCounter < minBits:
+        decoded = advance_frame(self)                     # preamble search / subframe sync, L493-533
+        if decoded is None:
             return
-        if not (self.trackFlags & TrackingFlags.SUBFRAME_SYNC):
-            idx = self.navBitsCounter - minBits
-            if not LNAV_CheckPreambule(self.navBitsBuffer[idx:idx + minBits]):
-                if self.navBitsCounter == self.navBitBufferSize:
-                    shifted = np.empty_like(self.navBitsBuffer)
-                    shifted[:-1] = self.navBitsBuffer[1:]
-                    self.navBitsBuffer = shifted
-                    self.navBitsCounter -= 1
-                return
-            if self.preambuleFound and idx == LNAV_SUBFRAME_SIZE:
-                self.trackFlags |= TrackingFlags.SUBFRAME_SYNC
-                logging.getLogger(__name__).debug(f"CID {self.channelID} subframe sync.")
-            else:
-                fresh = np.empty_like(self.navBitsBuffer)
-                fresh[minBits:] = 0
-                fresh[:minBits] = self.navBitsBuffer[idx:idx + 2 * LNAV_WORD_SIZE + 2]
-                self.navBitsBuffer = fresh
-                self.navBitsCounter = minBits
-                self.preambuleFound = True
-        if self.navBitsCounter < self.navBitBufferSize:
-            return
-        idx = self.navBitsCounter - minBits
-        if not LNAV_CheckPreambule(self.navBitsBuffer[idx:idx + 2 * LNAV_WORD_SIZE + 2]):
-            self.navBitsCounter = 0
-            self.trackFlags ^= TrackingFlags.SUBFRAME_SYNC
-            return
-        tow, subframeID, subframeBits = LNAV_DecodeTOW(self.navBitsBuffer[2:2 + LNAV_SUBFRAME_SIZE],
-                                                       self.navBitsBuffer[1])
+        tow, subframeID, subframeBits = decoded
         self.subframeFlags[subframeID - 1] = True
         self.codeSinceTOW = 0
         self.trackFlags |= TrackingFlags.TOW_DECODED
@@ -302,10 +276,6 @@ class ChannelL1CA(Channel):
         results["subframe_id"] = subframeID
         results["tow"] = tow
         results["bits"] = subframeBits
-        fresh = np.empty_like(self.navBitsBuffer)
-        fresh[:minBits] = self.navBitsBuffer[idx:idx + minBits]
-        self.navBitsBuffer = fresh
-        self.navBitsCounter = minBits
         self.tow = tow
         self.tow += self.navBitsCounter * LNAV_MS_PER_BIT * 1e-3
         logging.getLogger(__name__).debug(f"CID {self.channelID} subframe {subframeID} decoded "

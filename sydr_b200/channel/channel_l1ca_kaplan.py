@@ -23,6 +23,7 @@ from ..utils.circularbuffer import CircularBuffer
 from ..utils.constants import (GPS_L1CA_CODE_FREQ, GPS_L1CA_CODE_SIZE_BITS, LNAV_MS_PER_BIT, LNAV_SUBFRAME_SIZE,
                                LNAV_WORD_SIZE, TWO_PI, W0_BANDWIDTH_1, W0_BANDWIDTH_2, W0_SCALE_A2)
 from ..utils.enumerations import ChannelMessage, ChannelState, LoopLockState, TrackingFlags
+from .lnav_frame import advance_frame
 from .channel_l1ca_borre import ChannelL1CA
 
 
@@ -298,40 +299,11 @@ class ChannelL1CA_Kaplan(ChannelL1CA):
         return True
 
     def decodeSubframe(self):
-        minBits = 2 + 2 * LNAV_WORD_SIZE
-        if self.navBitsCounter < minBits:
+        """channel_l1ca_kaplan.py:760-823 (the search itself: lnav_frame.advance_frame)."""
+        decoded = advance_frame(self)
+        if decoded is None:
             return False
-        if not (self.trackFlags & TrackingFlags.SUBFRAME_SYNC):
-            idx = self.navBitsCounter - minBits
-            if not LNAV_CheckPreambule(self.navBitsBuffer[idx:idx + minBits]):
-                if self.navBitsCounter == self.navBitBufferSize:
-                    shifted = np.empty_like(self.navBitsBuffer)
-                    shifted[:-1] = self.navBitsBuffer[1:]
-                    self.navBitsBuffer = shifted
-                    self.navBitsCounter -= 1
-                return False
-            if self.preambuleFound and idx == LNAV_SUBFRAME_SIZE:
-                self.trackFlags |= TrackingFlags.SUBFRAME_SYNC
-            else:
-                fresh = np.empty_like(self.navBitsBuffer)
-                fresh[minBits:] = 0
-                fresh[:minBits] = self.navBitsBuffer[idx:idx + 2 * LNAV_WORD_SIZE + 2]
-                self.navBitsBuffer = fresh
-                self.navBitsCounter = minBits
-                self.preambuleFound = True
-        if self.navBitsCounter < self.navBitBufferSize:
-            return False
-        idx = self.navBitsCounter - minBits
-        if not LNAV_CheckPreambule(self.navBitsBuffer[idx:idx + 2 * LNAV_WORD_SIZE + 2]):
-            self.navBitsCounter = 0
-            self.trackFlags ^= TrackingFlags.SUBFRAME_SYNC
-            return False
-        self.tow, self.subframeID, self.subframeBits = LNAV_DecodeTOW(
-            self.navBitsBuffer[2:2 + LNAV_SUBFRAME_SIZE], self.navBitsBuffer[1])
-        fresh = np.empty_like(self.navBitsBuffer)
-        fresh[:minBits] = self.navBitsBuffer[idx:idx + minBits]
-        self.navBitsBuffer = fresh
-        self.navBitsCounter = minBits
+        self.tow, self.subframeID, self.subframeBits = decoded
         self.tow += self.navBitsCounter * LNAV_MS_PER_BIT * 1e-3
         return True
 

@@ -499,6 +499,94 @@ def g_decoding(R):
          p2b=np.array([RD.Prompt2Bit(v) for v in (-3.0, 0.0, 2.5)]))
 
 
+def lnav_stream(seed=5, n_subframes=4, lead=37, corrupt_at=None):
+    """A navigation bit stream as received: `lead` random bits, then subframes of ten parity-clean words
+    (TLM with the preamble, HOW with a TOW count and subframe id, eight data words), optionally one bit
+    flipped.  Polarity inverted as a Costas loop may deliver it."""
+    from sydr_b200.dsp.decoding import _PARITY_TAPS
+    rng = np.random.default_rng(seed)
+
+    def word(prev2, data24):
+        src = list(prev2) + list(data24)
+        par = []
+        for taps in _PARITY_TAPS:
+            b = 0
+            for t in taps:
+                b ^= src[t]
+            par.append(b)
+        return [int(b) ^ int(prev2[1]) for b in data24] + par
+
+    bits = [int(v) for v in rng.integers(0, 2, lead)]
+    prev = bits[-2:]
+    tow0 = 34567
+    for k in range(n_subframes):
+        tlm = [1, 0, 0, 0, 1, 0, 1, 1] + [int(v) for v in rng.integers(0, 2, 16)]
+        tow = [(tow0 + k) >> (16 - i) & 1 for i in range(17)]
+        how = tow + [0, 0] + [((k % 5) + 1) >> (2 - i) & 1 for i in range(3)] + [0, 0]
+        words = [tlm, how] + [[int(v) for v in rng.integers(0, 2, 24)] for _ in range(8)]
+        for w in words:
+            enc = word(prev, w)
+            bits += enc
+            prev = enc[-2:]
+    bits = np.array(bits, dtype=np.int64)
+    if corrupt_at is not None:
+        bits[corrupt_at] ^= 1
+    return 1 - bits                                              # inverted polarity
+
+
+def drive_decoding(ch, flags_cls, bits):
+    """Feed navigation bits to a Borre-style channel's runDecoding: 20 prompts per bit, bit synchronised."""
+    ch.trackFlags |= flags_cls.BIT_SYNC
+    rows, found = [], []
+    for k, b in enumerate(bits):
+        for ms in range(20):
+            ch.nbPrompt = 1
+            ch.correlatorsBuffer[0, 2] = 1000.0 if b else -1000.0
+            r = ch.runDecoding()
+            if r is not None:
+                found.append([k, int(r["subframe_id"]), int(r["tow"])] + [int(c) for c in r["bits"]])
+        rows.append([ch.navBitsCounter, int(ch.trackFlags), int(ch.preambuleFound), float(ch.tow), ch.codeSinceTOW])
+    return np.array(rows, dtype=np.float64), np.array(found, dtype=np.int64)
+
+
+def g_framing(R):
+    """Subframe synchronisation of the live reference channel (channel_l1ca_borre.py:455-573) on synthetic
+    LNAV bit streams: per-bit navBitsCounter / flags / preambuleFound / tow, and the decoded subframes."""
+    C = ref_import.load_channel()
+    out = {}
+    cases = {"clean": dict(seed=5, n_subframes=4, lead=37), "late": dict(seed=6, n_subframes=4, lead=401),
+             "broken": dict(seed=7, n_subframes=5, lead=12, corrupt_at=12 + 300 * 2 + 3)}
+    for name, kw in cases.items():
+        bits = lnav_stream(**kw)
+        cfg = {"filepath": "none", "sampling_frequency": "4e6", "is_complex": "true", "intermediate_frequency": "0.0",
+               "data_size": "8"}
+        rf = C.RFSignal(cfg)
+        buf = C.CircularBuffer(400000, np.complex128)
+        acq_cfg = {"doppler_range": "5000", "doppler_steps": "250", "coherent_integration": "1",
+                   "non_coherent_integration": "10", "threshold": "1.5"}
+        ch = C.ChannelL1CA(0, buf, None, rf, {"ACQUISITION": acq_cfg, "TRACKING": TRK_CFG})
+        ch.setSatellite(5)
+        rows, found = drive_decoding(ch, C.TrackingFlags, bits)
+        out[f"rows_{name}"], out[f"found_{name}"] = rows, found
+        print(f"  framing {name}: {len(bits)} bits, {len(found)} subframes decoded, final flags {int(ch.trackFlags)}")
+        # the Kaplan channel's decoding on the same stream (channel_l1ca_kaplan.py:725-861)
+        K = ref_import.load_channel_kaplan()
+        kch = K.ChannelL1CA_Kaplan(0, K.CircularBuffer(400000, np.complex128), None, K.RFSignal(cfg),
+                                   {"ACQUISITION": acq_cfg, "TRACKING": KAPLAN_TRK_CFG})
+        kch.setSatellite(5)
+        kch.trackFlags |= K.TrackingFlags.BIT_SYNC
+        kfound, krows = [], []
+        for k, b in enumerate(bits):
+            for ms in range(20):
+                kch.correlatorsResults[kch.IDX_I_PROMPT] = 1000.0 if b else -1000.0
+                r = kch.runDecoding()
+                if r is not None:
+                    kfound.append([k, int(r["subframe_id"]), int(r["tow"])] + [int(c) for c in r["bits"]])
+            krows.append([kch.navBitsCounter, int(kch.trackFlags), float(kch.tow), kch.codeSinceTOW])
+        out[f"kfound_{name}"], out[f"krows_{name}"] = np.array(kfound, dtype=np.int64), np.array(krows, dtype=np.float64)
+    save("framing.npz", **out)
+
+
 TRK_CFG = {
     "correlator_early": "-0.5", "correlator_prompt": "0", "correlator_late": "0.5",
     "dll_damping_ratio": "0.7", "dll_noise_bandwidth": "1.0", "dll_loop_gain": "1.0", "dll_pdi": "0.001",
@@ -512,7 +600,7 @@ def main():
     a = ap.parse_args()
     R = ref_import.load()
     groups = {"codes": g_codes, "peaks": g_peaks, "acq": g_acq, "epl": g_epl, "loop": g_loop, "channel": g_channel,
-              "kaplan": g_kaplan, "nav": g_nav, "database": g_database,
+              "kaplan": g_kaplan, "nav": g_nav, "database": g_database, "framing": g_framing,
               "decoding": g_decoding}
     for name, fn in groups.items():
         if a.only and name not in a.only and not (name == "acq" and any(o in ACQ_CASES for o in a.only)):

@@ -121,3 +121,52 @@ def test_new_struct_layouts():
     from sydr_b200 import _lib as L
     assert L.NAV_STATE_DTYPE.itemsize == 48 and L.NAV_STATE_DTYPE.fields["nav_count"][1] == 40
     assert C.sizeof(L.TrkConfig) == 48 and L.TrkConfig.iq_base.offset == 32 and L.TrkConfig.use_iq_base.offset == 40
+
+
+def _borre_channel():
+    from sydr_b200.channel.channel_l1ca_borre import ChannelL1CA
+    from sydr_b200.signal.rfsignal import RFSignal
+    from sydr_b200.utils.circularbuffer import CircularBuffer
+    import make_golden as MG
+    rf = RFSignal({"filepath": "none", "sampling_frequency": "4e6", "is_complex": "true",
+                   "intermediate_frequency": "0.0", "data_size": "8"})
+    acq = {"doppler_range": "5000", "doppler_steps": "250", "coherent_integration": "1",
+           "non_coherent_integration": "10", "threshold": "1.5"}
+    return rf, acq, MG, ChannelL1CA, CircularBuffer
+
+
+@pytest.mark.parametrize("case,kw", [("clean", dict(seed=5, n_subframes=4, lead=37)),
+                                     ("late", dict(seed=6, n_subframes=4, lead=401)),
+                                     ("broken", dict(seed=7, n_subframes=5, lead=12, corrupt_at=12 + 300 * 2 + 3))])
+def test_subframe_synchronisation_follows_reference_channel(golden, monkeypatch, case, kw):
+    """Preamble search, subframe sync, loss of sync and TOW decoding (channel_l1ca_borre.py:455-573) on
+    synthetic LNAV streams: per-bit counters / flags / tow and every decoded subframe of the live
+    reference channel (tests/golden/framing.npz); the Kaplan class decodes the same subframes."""
+    from sydr_b200.channel.channel_l1ca_kaplan import ChannelL1CA_Kaplan
+    from sydr_b200.utils.enumerations import TrackingFlags
+    from oracle import sydr_oracle as O
+    import sydr_b200.channel.channel_l1ca_borre as B
+    monkeypatch.setattr(B, "GenerateGPSGoldCode", lambda prn, samplingFrequency=None: O.ca_code(int(prn)))   # no GPU here
+    g = golden("framing.npz")
+    rf, acq, MG, ChannelL1CA, CircularBuffer = _borre_channel()
+    bits = MG.lnav_stream(**kw)
+    ch = ChannelL1CA(0, CircularBuffer(400000, np.complex128), None, rf, {"ACQUISITION": acq, "TRACKING": MG.TRK_CFG})
+    ch.setSatellite(5)
+    rows, found = MG.drive_decoding(ch, TrackingFlags, bits)
+    assert np.array_equal(rows, g[f"rows_{case}"]) and np.array_equal(found, g[f"found_{case}"])
+    assert len(found) >= 2
+    # Kaplan variant: same frame logic behind decodeBit / decodeSubframe / postDecodingUpdate
+    kch = ChannelL1CA_Kaplan(0, CircularBuffer(400000, np.complex128), None, rf,
+                             {"ACQUISITION": acq, "TRACKING": MG.KAPLAN_TRK_CFG})
+    kch.setSatellite(5)
+    kch.trackFlags |= TrackingFlags.BIT_SYNC
+    kfound, krows = [], []
+    for k, b in enumerate(bits):
+        for ms in range(20):
+            kch.correlatorsResults[kch.IDX_I_PROMPT] = 1000.0 if b else -1000.0
+            r = kch.runDecoding()
+            if r is not None:
+                kfound.append([k, int(r["subframe_id"]), int(r["tow"])] + [int(c) for c in r["bits"]])
+        krows.append([kch.navBitsCounter, int(kch.trackFlags), float(kch.tow), kch.codeSinceTOW])
+    assert np.array_equal(np.array(kfound, dtype=np.int64), g[f"kfound_{case}"])         # the live reference Kaplan channel
+    assert np.array_equal(np.array(krows, dtype=np.float64), g[f"krows_{case}"])
