@@ -309,6 +309,13 @@ int sydr_nav_bits(const sydr_trk_epoch* d_epochs, int max_epochs, const int* d_n
                   sydr_nav_state* d_nav, int n_channels, signed char* d_bits, double* d_bit_sums,
                   int max_bits, int* d_nbits, void* stream);
 
+/* The same for records of sydr_trk_run_kaplan: the Kaplan channel's rule (channel_l1ca_kaplan.py:555-566,
+ * 725-758) - BIT_SYNC as raised by its trackingStateUpdate (d_kepochs[..].flags & 2), sums starting
+ * with the synchronisation epoch's own prompt. */
+int sydr_nav_bits_kaplan(const sydr_trk_epoch* d_epochs, const sydr_kaplan_epoch* d_kepochs, int max_epochs,
+                         const int* d_nepochs, int first_epoch, sydr_nav_state* d_nav, int n_channels,
+                         signed char* d_bits, double* d_bit_sums, int max_bits, int* d_nbits, void* stream);
+
 /* ------------------------------------------------------------------ legacy C ABI ----- */
 /* The per-call entry points the reference's ctypes callers bind
  * (sydr/old/tracking/tracking_epl_c.py:31-96, sydr/old/acquisition/acquisition_pcps_c.py:32-66),

@@ -533,3 +533,24 @@ class KaplanTrackOracle:
                     cn0=self.cn0, pll_lock=self.pll_lock, fll_lock=self.fll_lock, lock_state=self.state,
                     flags=self.flags, rem_code=self.rem_code, rem_carrier=self.rem_carrier, n=n, n_req=self.n_req,
                     cur=self.cur)
+
+
+def nav_bits_kaplan(i_prompts, bit_sync_flags):
+    """The Kaplan channel's decodeBit (sydr/channel/channel_l1ca_kaplan.py:725-758) over a sequence of epochs:
+    `bit_sync_flags[k]` = BIT_SYNC after epoch k's trackingStateUpdate.  Returns bits, their sums, the
+    synchronisation epoch, and the pending (sum, count)."""
+    bits, sums, sync = [], [], -1
+    nav_sum, count = 0.0, 0
+    for k, (ip, fl) in enumerate(zip(i_prompts, bit_sync_flags)):
+        if not fl:                                                              # L733-737
+            nav_sum, count = 0.0, 0
+            continue
+        if sync < 0:
+            sync = k
+        nav_sum += float(ip)                                                    # L740-741
+        count += 1
+        if count == LNAV_MS_PER_BIT:                                            # L744-752
+            bits.append(1 if nav_sum > 0 else 0)
+            sums.append(nav_sum)
+            nav_sum, count = 0.0, 0
+    return np.array(bits, dtype=np.int8), np.array(sums, dtype=np.float64), sync, (nav_sum, count)

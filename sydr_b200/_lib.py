@@ -128,6 +128,7 @@ SIGNATURES = {
     "sydr_acq_handoff": (_i, [_vp, _i, _d, _d, _d, _ll, _ll, _ll, _d, _vp, _ll, _vp, _i, _vp, _vp]),
     "sydr_nav_state_init": (_i, [_vp]),
     "sydr_nav_bits": (_i, [_vp, _i, _vp, _i, _vp, _i, _vp, _vp, _i, _vp, _vp]),
+    "sydr_nav_bits_kaplan": (_i, [_vp, _vp, _i, _vp, _i, _vp, _i, _vp, _vp, _i, _vp, _vp]),
     # legacy per-call ABI (sydr/c_functions/*.c)
     "generateReplica": (None, [_vp, _sz, _d, _d, _vp, _vp]),
     "getCorrelator": (None, [_vp, _vp, _vp, _sz, _d, _d, _d, _vp, _vp]),

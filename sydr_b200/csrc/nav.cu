@@ -33,7 +33,11 @@ constexpr int kIPromptSlot = 2;               // corr[2] of sydr_trk_epoch
 
 __device__ __forceinline__ int np_sign(double x) { return (x > 0.0) - (x < 0.0); }   // np.sign of a finite value
 
+// kflags != NULL selects the Kaplan channel's rule (channel_l1ca_kaplan.py:555-566, 725-758): BIT_SYNC is the
+// flag its trackingStateUpdate raised (bit 2 of the device records' `flags`), and the 20-epoch sums start with
+// the synchronisation epoch's own prompt.
 __global__ void __launch_bounds__(32) nav_bits_kernel(const sydr_trk_epoch* __restrict__ epochs, int max_epochs,
+                                                      const sydr_kaplan_epoch* __restrict__ kepochs,
                                                       const int* __restrict__ nepochs, int first,
                                                       sydr_nav_state* __restrict__ nav, int8_t* __restrict__ bits,
                                                       double* __restrict__ bit_sums, int max_bits,
@@ -54,9 +58,13 @@ __global__ void __launch_bounds__(32) nav_bits_kernel(const sydr_trk_epoch* __re
             const int kk = base + lane;
             bool hit = false;
             if (kk < n) {
-                const long long cc = s.code_counter + kk;                 // codeCounter when epoch kk is ingested
-                const double prev = (kk == 0) ? s.prev_iprompt : ip(kk - 1);
-                hit = (cc >= 1) && (cc > kMinConvergence) && (np_sign(prev) != np_sign(ip(kk)));
+                if (kepochs != nullptr) {
+                    hit = (kepochs[(long long)ch * max_epochs + first + kk].flags & 2) != 0;
+                } else {
+                    const long long cc = s.code_counter + kk;             // codeCounter when epoch kk is ingested
+                    const double prev = (kk == 0) ? s.prev_iprompt : ip(kk - 1);
+                    hit = (cc >= 1) && (cc > kMinConvergence) && (np_sign(prev) != np_sign(ip(kk)));
+                }
             }
             const unsigned m = __ballot_sync(full, hit);
             if (m) ks = base + __ffs(m) - 1;
@@ -75,9 +83,15 @@ __global__ void __launch_bounds__(32) nav_bits_kernel(const sydr_trk_epoch* __re
             return;
         }
         s.sync_epoch = s.code_counter + ks;
-        s.nav_sum = s.row19;                                              // L471: correlatorsBuffer[-1]
-        s.nav_count = 1;
-        k = ks + 1;
+        if (kepochs != nullptr) {                                         // Kaplan: the sync epoch's own prompt is the first addend
+            s.nav_sum = 0.0;
+            s.nav_count = 0;
+            k = ks;
+        } else {
+            s.nav_sum = s.row19;                                          // L471: correlatorsBuffer[-1]
+            s.nav_count = 1;
+            k = ks + 1;
+        }
     }
 
     // ---- L471-483: 20 prompts per bit.  Bit j of this call ends at local epoch e_j (exclusive).
@@ -138,7 +152,7 @@ int sydr_nav_bits(const sydr_trk_epoch* d_epochs, int max_epochs, const int* d_n
     SYDR_REQUIRE(d_epochs && d_nepochs && d_nav && d_bits && d_nbits, SYDR_ERR_ARG, "NULL pointer");
     SYDR_REQUIRE(max_epochs > 0 && max_bits > 0 && first_epoch >= 0, SYDR_ERR_ARG, "sizes must be positive");
     if (n_channels <= 0) return SYDR_OK;
-    nav_bits_kernel<<<n_channels, 32, 0, (cudaStream_t)stream>>>(d_epochs, max_epochs, d_nepochs, first_epoch, d_nav,
+    nav_bits_kernel<<<n_channels, 32, 0, (cudaStream_t)stream>>>(d_epochs, max_epochs, nullptr, d_nepochs, first_epoch, d_nav,
                                                                  reinterpret_cast<int8_t*>(d_bits), d_bit_sums,
                                                                  max_bits, d_nbits);
     count_launch();
@@ -147,6 +161,20 @@ int sydr_nav_bits(const sydr_trk_epoch* d_epochs, int max_epochs, const int* d_n
 }
 
 }  // extern "C"
+
+extern "C" int sydr_nav_bits_kaplan(const sydr_trk_epoch* d_epochs, const sydr_kaplan_epoch* d_kepochs, int max_epochs,
+                                    const int* d_nepochs, int first_epoch, sydr_nav_state* d_nav, int n_channels,
+                                    signed char* d_bits, double* d_bit_sums, int max_bits, int* d_nbits, void* stream) {
+    SYDR_REQUIRE(d_epochs && d_kepochs && d_nepochs && d_nav && d_bits && d_nbits, SYDR_ERR_ARG, "NULL pointer");
+    SYDR_REQUIRE(max_epochs > 0 && max_bits > 0 && first_epoch >= 0, SYDR_ERR_ARG, "sizes must be positive");
+    if (n_channels <= 0) return SYDR_OK;
+    sydr::nav_bits_kernel<<<n_channels, 32, 0, (cudaStream_t)stream>>>(d_epochs, max_epochs, d_kepochs, d_nepochs, first_epoch,
+                                                                       d_nav, reinterpret_cast<int8_t*>(d_bits), d_bit_sums,
+                                                                       max_bits, d_nbits);
+    sydr::count_launch();
+    SYDR_CUDA_CHECK(cudaGetLastError());
+    return SYDR_OK;
+}
 
 // ------------------------------------------------------------------------------------------
 // K-HAND: acquisition -> tracking hand-off on the device.

@@ -356,8 +356,16 @@ class NavBitEngine:
                                        _stream_ptr(stream)), "sydr_nav_bits")
 
     def launch(self, trk: "TrackingEngine", first_epoch=0, stream=None):
-        """Consume records [first_epoch, n) of every channel of `trk` (enqueue after trk.launch)."""
+        """Consume records [first_epoch, n) of every channel of `trk` (enqueue after trk.launch).  A
+        KaplanTrackingEngine's records are read with the Kaplan channel's bit-synchronisation rule."""
         assert trk.n_ch >= self.n_ch                      # the first n_ch slots of the tracking engine
+        if hasattr(trk, "_kout"):
+            L.check(L.load().sydr_nav_bits_kaplan(trk._out.data_ptr(), trk._kout.data_ptr(), trk.max_epochs,
+                                                  trk._nep.data_ptr(), int(first_epoch), self._state.data_ptr(),
+                                                  self.n_ch, self._bits.data_ptr(), self._sums.data_ptr(),
+                                                  self.max_bits, self._nbits.data_ptr(), _stream_ptr(stream)),
+                    "sydr_nav_bits_kaplan")
+            return
         self.launch_records(trk._out, trk.max_epochs, trk._nep, first_epoch, stream)
 
     def states(self) -> np.ndarray:

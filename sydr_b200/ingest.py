@@ -147,7 +147,7 @@ class StreamingReceiver:
         self.loop = str(loop)                  # "borre" or "kaplan": which loop closure the tracking kernel runs
         if self.loop not in ("borre", "kaplan"):
             raise L.SydrError(f"unknown loop closure '{loop}'")
-        self.want_records, self.want_bits = bool(want_records), bool(want_bits and self.loop == "borre")
+        self.want_records, self.want_bits = bool(want_records), bool(want_bits)
         self.reader_threads = int(reader_threads)
         self.trk_cfg = dict(cluster=cluster, threads=threads, use_tma=use_tma)
         self.acq = AcquisitionEngine(self.fs, float(rf.interFrequency), doppler_range, doppler_step, coh, noncoh,
@@ -193,6 +193,8 @@ class StreamingReceiver:
                                   for _ in range(2)]
                 self._krec_host = [torch.empty(n_ch * self.max_epochs * 40, dtype=torch.uint8, pin_memory=True)
                                    for _ in range(2)]
+                if self.want_bits:
+                    self._nav = NavBitEngine(n_ch, max_bits=self.max_epochs // 20 + 2, device=self.device)
                 return chans
             states = make_trk_states(self.fs, chans, self.channel_cfg)
             if self._trk is not None and self._trk.n_ch == n_ch:        # a receiver that is run again keeps its buffers

@@ -335,6 +335,28 @@ def g_nav(R):
         out[f"epochs_{prn}"] = np.array(rows, dtype=np.float64)
         out[f"bits_{prn}"] = np.array(ch.navBitsBuffer[:ch.navBitsCounter], dtype=np.int8)
         print(f"  nav PRN {prn}: {len(rows)} epochs, {ch.navBitsCounter} bits")
+    # the Kaplan channel's bit accumulation on the same recording (channel_l1ca_kaplan.py:725-758): BIT_SYNC comes
+    # from trackingStateUpdate, the sums start with the synchronisation epoch's own prompt
+    K = ref_import.load_channel_kaplan()
+    for prn in prns:
+        cfg = {"filepath": "none", "sampling_frequency": str(fs), "is_complex": "true",
+               "intermediate_frequency": "0.0", "data_size": "8"}
+        rf = K.RFSignal(cfg)
+        spm = rf.samplesPerMs
+        buf = K.CircularBuffer(int(fs * 1e-3 * 100), np.complex128)
+        ch = K.ChannelL1CA_Kaplan(0, buf, None, rf, {"ACQUISITION": acq_cfg, "TRACKING": KAPLAN_TRK_CFG})
+        ch.setSatellite(prn)
+        rows = []
+        for tick in range(ms):
+            buf.shift(x[tick * spm:(tick + 1) * spm])
+            for r in ch._processHandler():
+                if r["type"] == K.ChannelMessage.TRACKING_UPDATE:
+                    rows.append([r["i_prompt"], ch.navPromptSum, ch.navPromptSumCounter, ch.navBitsCounter,
+                                 float(int(ch.trackFlags) & 3)])
+        assert ch.navBitsCounter < 62
+        out[f"kepochs_{prn}"] = np.array(rows, dtype=np.float64)
+        out[f"kbits_{prn}"] = np.array(ch.navBitsBuffer[:ch.navBitsCounter], dtype=np.int8)
+        print(f"  nav (Kaplan) PRN {prn}: {len(rows)} epochs, {ch.navBitsCounter} bits")
     out["meta"] = np.array([fs, nbits, seed, ms, ds], dtype=np.float64)
     out["prns"] = np.array(prns)
     out["sha"] = sha(iq)

@@ -152,6 +152,17 @@ def test_receiver_with_the_kaplan_ini(tmp_path):
         cfg["CHANNELS"]["gps_l1ca"] = os.path.join(H.ROOT, "config", "channels", "channel_GPS_L1CA_kaplan.ini")
         return cfg
 
+    # the streaming path with the Kaplan loops, bits included: equal to the oracle's rule on the same records
+    from sydr_b200.ingest import StreamingReceiver
+    from sydr_b200.signal.rfsignal import RFSignal
+    rx = StreamingReceiver(RFSignal(dict(config("x")["RFSIGNAL"])), [3, 19], 2, chunk_seconds=0.2, loop="kaplan",
+                           channel_cfg=H.MG.KAPLAN_TRK_CFG)
+    so = rx.run_all()
+    rx.close()
+    for r, k, bits in zip(so["epochs"], so["kaplan"], so["bits"]):
+        ob = O.nav_bits_kaplan(r["corr"][:, 2], (k["flags"] & 2) != 0)[0]
+        assert np.array_equal(bits, ob)
+    assert max(len(b_) for b_ in so["bits"]) >= 10
     b = ReceiverGPSL1CA(config("fast"), overwrite=True)
     assert b.channelClass.__name__ == "ChannelL1CA_Kaplan"
     b.run_fast(chunk_seconds=0.2)

@@ -181,3 +181,45 @@ def test_pipeline_with_nothing_to_track():
     assert out["channels"] == [] and out["epochs"] == [] and len(out["peaks"]) == 4
     assert (pipe._trk.states()["status"] == 1).all()
     pipe.close()
+
+
+@pytest.mark.parametrize("cuts", [None, (7, 333, 334, 900)])
+def test_nav_bits_kaplan_rule(golden, cuts):
+    """K-NAV with the Kaplan channel's rule on the live reference Kaplan channel's prompts and flags
+    (tests/golden/nav.npz): bits bit-exact, sums and pending state equal to the oracle's, any chunking."""
+    import torch
+    from sydr_b200 import _lib as L
+    from sydr_b200.engine import NavBitEngine
+    g = golden("nav.npz")
+    prns = [int(p) for p in g["prns"]]
+    eps = [g[f"kepochs_{p}"] for p in prns]
+    n = max(len(e) for e in eps)
+    bounds = [n] if cuts is None else list(cuts) + [n]
+    eng = NavBitEngine(len(prns), max_bits=128)
+    bits = [[] for _ in prns]
+    sums = [[] for _ in prns]
+    lo = 0
+    for hi in bounds:
+        m = hi - lo
+        rec = np.zeros((len(prns), m), dtype=L.TRK_EPOCH_DTYPE)
+        krec = np.zeros((len(prns), m), dtype=L.KAPLAN_EPOCH_DTYPE)
+        for c, e in enumerate(eps):
+            rec["corr"][c, :, 2] = e[lo:hi, 0]
+            krec["flags"][c] = e[lo:hi, 4].astype(np.int32)
+        d_rec = torch.from_numpy(rec.view(np.uint8).reshape(-1)).cuda()
+        d_k = torch.from_numpy(krec.view(np.uint8).reshape(-1)).cuda()
+        d_nep = torch.full((len(prns),), m, dtype=torch.int32).cuda()
+        L.check(L.load().sydr_nav_bits_kaplan(d_rec.data_ptr(), d_k.data_ptr(), m, d_nep.data_ptr(), 0,
+                                              eng._state.data_ptr(), len(prns), eng._bits.data_ptr(), eng._sums.data_ptr(),
+                                              eng.max_bits, eng._nbits.data_ptr(), 0))
+        for c, (b, s) in enumerate(eng.fetch()):
+            bits[c].extend(b.tolist())
+            sums[c].extend(s.tolist())
+        lo = hi
+    st = eng.states()
+    for c, p in enumerate(prns):
+        e = eps[c]
+        ob, osum, osync, (pend, cnt) = O.nav_bits_kaplan(e[:, 0], e[:, 4] >= 2)
+        assert bits[c] == g[f"kbits_{p}"].tolist() == ob.tolist()
+        assert sums[c] == osum.tolist()
+        assert int(st["sync_epoch"][c]) == osync and int(st["nav_count"][c]) == cnt and st["nav_sum"][c] == pend

@@ -138,6 +138,16 @@ def test_nav_bit_oracle_matches_reference_channel(golden):
     assert sync > 100 and len(b) == len(s)
 
 
+def test_kaplan_nav_bit_oracle_matches_reference_channel(golden):
+    g = golden("nav.npz")
+    for prn in g["prns"]:
+        ep, bits = g[f"kepochs_{prn}"], g[f"kbits_{prn}"]
+        b, s, sync, (pend, cnt) = O.nav_bits_kaplan(ep[:, 0], ep[:, 4] >= 2)
+        assert np.array_equal(b, bits)
+        assert pend == ep[-1, 1] and cnt == ep[-1, 2] and len(b) == ep[-1, 3]
+    assert len(g["kbits_22"]) >= 40 and len(g["kbits_7"]) == 0          # one channel never reaches bit sync in 1.3 s
+
+
 def test_kaplan_loop_oracle_matches_reference_channel(golden):
     """KaplanTrackOracle (FLL-assisted PLL, lock indicators, C/N0, PULL_IN/WIDE/NARROW, code lock, bit
     sync) teacher-forced with the live reference channel's correlator sums: every packet field of all
