@@ -192,7 +192,8 @@ typedef struct {
                                of 8 samples) and iq_len = w0 + len, so that `cur` and the
                                records' `start` stay recording-relative (streaming ingest)   */
     int32_t use_iq_base;
-    int32_t reserved;
+    int32_t dense;          /* 1 = register-lean instantiation of the latency kernel (3 CTAs per SM): a few
+                               per cent slower alone, denser when several launches share the GPU    */
 } sydr_trk_config;
 
 /* Closed-loop Borre tracking (runTracking, channel_l1ca_borre.py:333-451: EPL +

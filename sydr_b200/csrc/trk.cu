@@ -853,6 +853,7 @@ struct TrkParams {
     double acc_inv;          // 1 / acc_scale
     int resume;              // follow-up of a LEAN launch: continue the record rows, serve kNeedGeneral channels
     long long* prof;         // optional [n_channels][16] phase cycle counters of thread 0 (NULL = off)
+    int dense;               // DENSE instantiation requested (steps in flight share the GPU)
     sydr_kaplan_state* kstates;   // Kaplan loop closure (KAP instantiation): per-channel state and per-epoch extras
     sydr_kaplan_epoch* kout;
 };
@@ -866,6 +867,7 @@ struct EpochCtl {            // published by warps 0 / 1 for every epoch
 constexpr int kMaxCluster = 8;
 constexpr int kWinTail = 32;     // samples staged beyond a CTA's window (segments that start inside may end outside)
 constexpr int kTrkMaxThreads = 384;
+constexpr int kDenseMaxThreads = 288;    // DENSE instantiation: <= 113 registers, three CTAs per SM beside other launches
 constexpr int kLeanThreads = 256;
 constexpr int kKaplanMaxThreads = 384;   // the Kaplan carrier warp holds more state: 170 registers per thread instead of 102
 constexpr int kNeedGeneral = 2;  // channel status: stopped in front of an epoch only the general kernel serves
@@ -1195,8 +1197,11 @@ __device__ __forceinline__ void carrier_close_kaplan(SH& sh, CarrierState& st, K
 // chain, so the production instantiation does not carry them).
 // KAP = the carrier warp closes the Kaplan loops (FLL-assisted PLL, lock indicators, C/N0, lock-state
 // machine) instead of the Borre PLL; the code loop and everything else are shared.
-template <int DT, int VPC, bool TMA, bool LEAN, bool PROF = false, bool KAP = false>
-__global__ void __launch_bounds__(LEAN ? kLeanThreads : (KAP ? kKaplanMaxThreads : kTrkMaxThreads), LEAN ? 3 : 1)
+// DENSE = same code under a tighter register budget (two CTAs of 288 threads per SM guaranteed, three of 192
+// in practice): 4 % slower alone, but launches of several steps in flight pack 3 per SM instead of 2.
+template <int DT, int VPC, bool TMA, bool LEAN, bool PROF = false, bool KAP = false, bool DENSE = false>
+__global__ void __launch_bounds__(LEAN ? kLeanThreads : (KAP ? kKaplanMaxThreads : (DENSE ? kDenseMaxThreads : kTrkMaxThreads)),
+                                  LEAN ? 3 : (DENSE ? 2 : 1))
 trk_borre_kernel(const TrkParams P) {
     constexpr int SPV = IqTraits<DT>::SPV, BPS = IqTraits<DT>::BPS;
     constexpr int C = SPV * VPC;
@@ -1545,6 +1550,9 @@ int launch_trk(const TrkParams& P, int n_channels, int cluster, int threads, int
     constexpr bool HAS_LEAN = SegTraits<DT, VPC>::NV > 0;
     auto kern = P.use_tma ? trk_borre_kernel<DT, VPC, true, false> : trk_borre_kernel<DT, VPC, false, false>;
     if (P.prof != nullptr) kern = P.use_tma ? trk_borre_kernel<DT, VPC, true, false, true> : trk_borre_kernel<DT, VPC, false, false, true>;
+    if (P.dense && threads <= kDenseMaxThreads && P.prof == nullptr && P.kstates == nullptr)
+        kern = P.use_tma ? trk_borre_kernel<DT, VPC, true, false, false, false, true>
+                         : trk_borre_kernel<DT, VPC, false, false, false, false, true>;
     if (P.kstates != nullptr)
         kern = P.use_tma ? trk_borre_kernel<DT, VPC, true, false, false, true> : trk_borre_kernel<DT, VPC, false, false, false, true>;
     size_t smem_launch = smem;
@@ -1765,6 +1773,7 @@ static int trk_run_impl(const void* d_iq, int iq_dtype, long long iq_alloc_sampl
     P.prof = g_trk_prof;
     P.kstates = d_kstates;
     P.kout = d_kout;
+    P.dense = cfg ? (cfg->dense != 0) : 0;
     cudaStream_t s = (cudaStream_t)stream;
     if (lean) {
         TrkParams PL = P;

@@ -28,7 +28,7 @@ def _mark():
 class ColdStartPipeline:
     def __init__(self, fs, nbits, search_prns, n_channels, doppler_range=5000.0, doppler_step=250.0, coh=1,
                  noncoh=10, max_seconds=2.0, inter_freq=0.0, threshold=1.5, channel_cfg=None, device=None,
-                 cluster=0, threads=0, use_tma=True, loop="borre"):
+                 cluster=0, threads=0, use_tma=True, loop="borre", dense=False):
         L.require_device()
         if device is not None:
             torch.cuda.set_device(device)
@@ -37,6 +37,7 @@ class ColdStartPipeline:
         self.n_channels, self.threshold = int(n_channels), float(threshold)
         self.channel_cfg = channel_cfg
         self.trk_cfg = dict(cluster=cluster, threads=threads, use_tma=use_tma)
+        self._dense = bool(dense)
         self.acq = AcquisitionEngine(fs, inter_freq, doppler_range, doppler_step, coh, noncoh, list(search_prns),
                                      device=self.device)
         self.max_samples = int(round(max_seconds * fs))
@@ -63,7 +64,8 @@ class ColdStartPipeline:
         idle = np.repeat(tmpl, self.n_channels)
         idle["status"] = 1
         if ktmpl is None:
-            self._trk = TrackingEngine(self.fs, idle, self.max_epochs, device=self.device, **self.trk_cfg)
+            self._trk = TrackingEngine(self.fs, idle, self.max_epochs, device=self.device, dense=self._dense,
+                                       **self.trk_cfg)
             self._ktmpl = None
         else:
             ks = np.repeat(ktmpl, self.n_channels)
@@ -219,6 +221,7 @@ class ColdStartPool:
     (5.7 -> 4.4 ms for the headline chunk)."""
 
     def __init__(self, lanes: int = 2, **pipeline_kwargs):
+        pipeline_kwargs.setdefault("dense", int(lanes) > 1)       # launches share the GPU: pack the tracking CTAs 3 per SM
         self.lanes = [ColdStartPipeline(**pipeline_kwargs) for _ in range(int(lanes))]
         dev = self.lanes[0].device
         self._streams = [torch.cuda.Stream(device=dev) for _ in self.lanes]
