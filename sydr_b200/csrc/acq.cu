@@ -14,6 +14,11 @@
 //     acq_fwd_kernel and shared by all PRNs (1/n_prn of the inverse-FFT work);
 //   * the coherent sum commutes with the linear transforms, so the coh periods are summed in
 //     the time domain before the single forward FFT;
+//   * Doppler bins that differ by a multiple of fs/N (1 kHz for a 1 ms code period) have the same
+//     forward spectrum, circularly shifted by that many bins (the extra carrier factor is
+//     exp(2 pi i q n / N)): with 250 Hz steps only 4 of the 41 rows are transformed, the others
+//     read a base row at a rotated index.  The forward spectra shrink from 82 MB to 8 MB at
+//     25 MS/s and stay in L2;
 //   * acq_ifft_kernel owns one (PRN, bin) row per CTA: spectrum multiply -> inverse FFT in
 //     shared memory -> magnitude -> non-coherent sum in registers -> arg-max / second peak
 //     with warp shuffles.  The correlation map is only written when the caller asks for it.
@@ -202,6 +207,8 @@ struct AcqDev {                 // device-side view of a plan
     const float2* tw;           // per-stage twiddle tables (Plan::TW* offsets), half-plan length
     const float2* tw_split;     // w_N^e, e < N/2 (HALVES == 2 only)
     int n_code, n_prn, n_rows, bin_lo, coh, noncoh, chip;
+    int n_base;                 // > 0: only the global Doppler rows 0 .. n_base-1 have forward spectra; global row R uses
+                                // row R % n_base circularly shifted by R / n_base bins (they differ by multiples of fs/N)
     double fs, inter_freq, doppler_range, doppler_step;
 };
 
@@ -215,7 +222,10 @@ __global__ void __launch_bounds__(P::T) acq_fwd_kernel(const AcqDev A, const voi
     const int cell = blockIdx.x / HALVES;        // (row, block)
     const int row = cell / A.noncoh, blk = cell - row * A.noncoh;
     // acquisition.py:34,42: freq = IF - bins[b], bins = arange(-range, range+1, step)
-    const double fbin = -A.doppler_range + (double)(A.bin_lo + row) * A.doppler_step;
+    // with shared spectra the transformed rows are the *global* rows 0 .. n_base-1, whatever Doppler range this
+    // plan owns: every shard of a multi-GPU search then works from identical base spectra
+    const int grow = (HALVES == 1 && A.n_base > 0) ? row : A.bin_lo + row;
+    const double fbin = -A.doppler_range + (double)grow * A.doppler_step;
     const double freq = A.inter_freq - fbin;
     const long long blk0 = (long long)blk * A.coh * NF;
 
@@ -345,10 +355,15 @@ __global__ void __launch_bounds__(P::T) acq_ifft_kernel(const AcqDev A, sydr_acq
         for (int r = 0; r < RL; ++r) acc[q][r] = 0.f;
 
     for (int blk = 0; blk < A.noncoh; ++blk) {
-        const float2* __restrict__ Y = A.Y + ((size_t)row * A.noncoh + blk) * NF;
+        // forward spectrum of this row: its own, or base row (row % n_base) read q = row / n_base bins lower
+        const int brow = (HALVES == 1 && A.n_base > 0) ? (A.bin_lo + row) % A.n_base : row;
+        const int qsh = (HALVES == 1 && A.n_base > 0) ? (A.bin_lo + row) / A.n_base : 0;
+        const float2* __restrict__ Y = A.Y + ((size_t)brow * A.noncoh + blk) * NF;
         // swapped product z = swap(Y[f] * C[f]); Y of a split transform is stored [parity][m]
         auto zin = [&](int f) -> float2 {
-            const float2 y = (HALVES == 2) ? __ldg(Y + (size_t)(f & 1) * NH + (f >> 1)) : __ldg(Y + f);
+            int fy = f - qsh;
+            fy += (fy < 0) ? NF : 0;
+            const float2 y = (HALVES == 2) ? __ldg(Y + (size_t)(f & 1) * NH + (f >> 1)) : __ldg(Y + fy);
             const float2 z = cmul(y, code_at(f));
             return make_float2(z.y, z.x);
         };
@@ -624,7 +639,8 @@ int launch_acq(sydr_acq_plan* pl, const void* d_iq, int dt, sydr_acq_row* d_rows
     {
         auto k = acq_fwd_kernel<P, HALVES>;
         SYDR_CUDA_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fft_bytes));
-        k<<<A.n_rows * A.noncoh * HALVES, P::T, fft_bytes, s>>>(A, d_iq, dt);
+        const int fwd_rows = (HALVES == 1 && A.n_base > 0) ? A.n_base : A.n_rows;
+        k<<<fwd_rows * A.noncoh * HALVES, P::T, fft_bytes, s>>>(A, d_iq, dt);
         count_launch();
         SYDR_CUDA_CHECK(cudaGetLastError());
     }
@@ -788,9 +804,16 @@ int sydr_acq_plan_create(double fs, double inter_freq, double doppler_range, dou
     const int n_rows = bin_hi - bin_lo;
     int rc = SYDR_OK;
     auto fail = [&](int code) { sydr_acq_plan_destroy(pl); return code; };
+    // rows R and R + G differ by G * step = fs / N when that ratio is a whole number: they share forward spectra
+    int n_base = 0;
+    {
+        const double g = (fs / (double)n_code) / doppler_step;
+        const int G = (int)llround(g);
+        n_base = (shape.halves == 1 && G >= 1 && fabs(g - (double)G) < 1e-9) ? G : 0;    // global base rows, whatever the shard
+    }
     if (cudaMalloc(&pl->d_prns, sizeof(int) * n_prn) != cudaSuccess ||
         cudaMalloc(&pl->d_code_spec, sizeof(float2) * (size_t)n_prn * n_code) != cudaSuccess ||
-        cudaMalloc(&pl->d_Y, sizeof(float2) * (size_t)n_rows * noncoh * n_code) != cudaSuccess ||
+        cudaMalloc(&pl->d_Y, sizeof(float2) * (size_t)(n_base > 0 ? n_base : n_rows) * noncoh * n_code) != cudaSuccess ||
         cudaMalloc(&pl->d_rows, sizeof(sydr_acq_row) * (size_t)n_prn * n_rows) != cudaSuccess) {
         set_error("acquisition plan: device allocation failed (%s)", cudaGetErrorString(cudaGetLastError()));
         return fail(SYDR_ERR_CUDA);
@@ -813,6 +836,7 @@ int sydr_acq_plan_create(double fs, double inter_freq, double doppler_range, dou
     A.code_spec = pl->d_code_spec; A.Y = pl->d_Y; A.tw = pl->d_tw; A.tw_split = pl->d_tw_split;
     A.n_code = n_code; A.n_prn = n_prn; A.n_rows = n_rows; A.bin_lo = bin_lo; A.coh = coh; A.noncoh = noncoh;
     A.chip = chip; A.fs = fs; A.inter_freq = inter_freq; A.doppler_range = doppler_range; A.doppler_step = doppler_step;
+    A.n_base = n_base;
     *out_plan = pl;
     return SYDR_OK;
 }
