@@ -326,7 +326,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--chunk-seconds", type=float, default=2.0)
-    ap.add_argument("--lanes", type=int, default=4, help="steps in flight per GPU (ColdStartPool)")
+    ap.add_argument("--lanes", type=int, default=5, help="steps in flight per GPU (ColdStartPool)")
     ap.add_argument("--cluster", type=int, default=0)
     ap.add_argument("--threads", type=int, default=0)
     ap.add_argument("--no-tma", action="store_true")

@@ -1720,7 +1720,8 @@ static int trk_run_impl(const void* d_iq, int iq_dtype, long long iq_alloc_sampl
         // Two thirds of a thread per chunk / segment: the epoch is a latency chain, not a throughput
         // problem (2.00 us with 192 threads, 2.01 with 288 at 25 MS/s), and the smaller CTA leaves
         // registers and issue slots to whatever shares the SM (other steps in flight, ColdStartPool).
-        const int want = (2 * Q + 2) / 3;
+        // (half a thread per segment in the DENSE shape: 160 threads at 25 MS/s, four CTAs per SM)
+        const int want = (cfg && cfg->dense) ? (Q + 1) / 2 : (2 * Q + 2) / 3;
         const int rounds = (want + kTrkMaxThreads - 1) / kTrkMaxThreads;
         threads = (((want + rounds - 1) / rounds) + 31) / 32 * 32;
         if (threads < 64) threads = 64;                    // warps 0 and 1 close the two loops
