@@ -34,8 +34,8 @@ FLOP_PER_SAMPLE_CH = 31.0
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the
 # `ncu --set full` capture of this very workload (tools/ncu_bench.py, 2 s chunk, 12 channels;
 # profiles/r1_ncu_summary.txt).  Algorithmic bytes of the same launch: 200.0 MB IQ + 3.07 MB records.
-NCU_TRAFFIC_BYTES = {"trk_borre_kernel": (199.375360e6 + 5.926912e6, 2.0),
-                     "acq_ifft_kernel": (88.481024e6 + 3.907328e6, None)}
+NCU_TRAFFIC_BYTES = {"trk_borre_kernel": (199.892992e6 + 5.809152e6, 2.0),
+                     "acq_ifft_kernel": (14.476032e6 + 0.0, None)}
 
 
 def f_acq(n):                                  # flop per (PRN, bin, code period), SURVEY.md §8(d)
