@@ -423,12 +423,12 @@ def main():
 
     # ---- warm-up, then K steps resident in HBM
     run_steps(args.warmup, lambda m: pool.submit_device(d_iq, m), False)
-    barrier()
     sampler = ClockSampler(local)
-    sampler.start()
+    sampler.start()                                     # (NVML start-up takes milliseconds: before the barrier)
     lib.sydr_reset_launch_count()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
     k_ev = []
+    barrier()                                           # every rank enters the timed region together
     ev[0].record()
     run_steps(args.steps, lambda m: pool.submit_device(d_iq, m), False, k_ev)
     barrier()
