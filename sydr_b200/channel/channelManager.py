@@ -25,7 +25,7 @@ import numpy as np
 import torch
 
 from .. import _lib as L
-from ..engine import AcquisitionEngine, TrackingEngine, make_trk_states
+from ..engine import (AcquisitionEngine, KaplanTrackingEngine, TrackingEngine, make_kaplan_states, make_trk_states)
 from ..signal.rfsignal import IQBlock, RFSignal
 from ..utils.circularbuffer import CircularBuffer
 from ..utils.enumerations import ChannelState
@@ -269,16 +269,31 @@ class ChannelManager:
         """Give the channel a slot in the device-side state array (all slots exist from the first
         use; idle ones carry status 1 and are skipped by the kernel)."""
         fs = self.rfSignal.samplingFrequency
+        kaplan = getattr(chan, "_deviceLoop", "borre") == "kaplan"
+        one = [dict(prn=int(chan.satelliteID), carrier_freq=chan.carrierFrequency,
+                    start_sample=self._abs_cur[chan.channelID] - self._base)]
         if self._trk is None:
-            idle = make_trk_states(fs, [dict(prn=1, carrier_freq=0.0, start_sample=0)] * self.nbChannels)
-            idle["status"] = 1
-            self._trk = TrackingEngine(fs, idle, self.MAX_QUEUED_EPOCHS, device=self.device)
+            dummy = [dict(prn=1, carrier_freq=0.0, start_sample=0)] * self.nbChannels
+            if kaplan:           # every channel of a manager runs the same loop closure (one class per receiver)
+                idle, kidle = make_kaplan_states(fs, dummy, chan._trackingConfiguration)
+                idle["status"] = 1
+                self._trk = KaplanTrackingEngine(fs, idle, kidle, self.MAX_QUEUED_EPOCHS, device=self.device)
+            else:
+                idle = make_trk_states(fs, dummy)
+                idle["status"] = 1
+                self._trk = TrackingEngine(fs, idle, self.MAX_QUEUED_EPOCHS, device=self.device)
             self._trk_slots = {cid: k for k, cid in enumerate(self.channels)}
+        if kaplan != isinstance(self._trk, KaplanTrackingEngine):
+            raise L.SydrError("a ChannelManager batches one loop closure: do not mix Borre and Kaplan channels")
         st = self._trk.states()
         slot = self._trk_slots[chan.channelID]
-        new = make_trk_states(fs, [dict(prn=int(chan.satelliteID), carrier_freq=chan.carrierFrequency,
-                                        start_sample=self._abs_cur[chan.channelID] - self._base)],
-                              chan._trackingConfiguration)
+        if kaplan:
+            new, knew = make_kaplan_states(fs, one, chan._trackingConfiguration)
+            ks = self._trk.kaplan_states()
+            ks[slot] = knew[0]
+            self._trk._kstates.copy_(torch.from_numpy(ks.view(np.uint8).reshape(-1)))
+        else:
+            new = make_trk_states(fs, one, chan._trackingConfiguration)
         new["epochs_done"] = 0
         st[slot] = new[0]
         self._trk.reset(st)
@@ -301,8 +316,10 @@ class ChannelManager:
         bad = [cid for cid, k in self._trk_slots.items() if st["status"][k] < 0]
         if bad:
             raise L.SydrError(f"tracking aborted on channels {bad} (NCO state left the supported range)")
+        kex = self._trk.fetch_kaplan() if isinstance(self._trk, KaplanTrackingEngine) else None
         for c in chans:
-            self._queues[c.channelID].extend(recs[self._trk_slots[c.channelID]])
+            k = self._trk_slots[c.channelID]
+            self._queues[c.channelID].extend(recs[k] if kex is None else list(zip(recs[k], kex[k])))
 
     def _due_epoch(self, chan):
         """The reference's per-tick rule (channel_l1ca_borre.py:347-349)."""
@@ -314,6 +331,13 @@ class ChannelManager:
         return q.pop(0)
 
     def _ingest(self, chan, rec):
+        if isinstance(rec, tuple):                      # Kaplan: (record, extras)
+            rec, kex = rec
+            n = int(rec["n"])
+            if n != chan.track_requiredSamples:
+                raise L.SydrError(f"CID {chan.channelID}: device epoch length {n} != host {chan.track_requiredSamples}")
+            self._abs_cur[chan.channelID] += n
+            return chan._ingestEpoch(rec, kex)
         n = int(rec["n"])
         if n != chan.track_requiredSamples:
             raise L.SydrError(f"CID {chan.channelID}: device epoch length {n} != host {chan.track_requiredSamples}")

@@ -90,6 +90,9 @@ class ChannelL1CA_Kaplan(ChannelL1CA):
         self.timeSinceLastState = 0
         self.loopLockState = LoopLockState.PULL_IN
         self.trackFlags = TrackingFlags.UNKNOWN
+        # for the batched dispatcher: the [TRACKING] values the device loop closure needs (sydr_kaplan_state)
+        self._trackingConfiguration = {k: float(v) for k, v in configuration.items()}
+        self._deviceLoop = "kaplan"
         self.remainingCode = 0.0
         self.remainingCarrier = 0.0
         self.codeStep = GPS_L1CA_CODE_FREQ / self.rfSignal.samplingFrequency
@@ -230,6 +233,45 @@ class ChannelL1CA_Kaplan(ChannelL1CA):
             return
         self.timeSinceLastState = 0
         logging.getLogger(__name__).debug(f"CID {self.channelID} tracking switched to {self.loopLockState}.")
+
+    def _ingestEpoch(self, rec, kex):
+        """Batched path (ChannelManager): take over one epoch closed on the device - the members
+        runTracking would have left (channel_l1ca_kaplan.py:342-619) - and build its packet.  `rec` is the
+        sydr_trk_epoch record, `kex` its sydr_kaplan_epoch extras."""
+        self.correlatorsResults[:] = rec["corr"]
+        if self.correlatorsAccumCounter == LNAV_MS_PER_BIT:
+            self.correlatorsAccumCounter = 0
+            self.correlatorsAccum[:] = 0.0
+        self.correlatorsAccum += self.correlatorsResults
+        self.correlatorsAccumCounter += 1
+        self.dllDiscrim = float(rec["code_err"])
+        self.pllDiscrim = float(rec["carrier_err"])
+        self.fllDiscrim = float(kex["fll"])
+        self.carrierFrequencyError = float(rec["pll"])
+        self.codeFrequencyError = float(rec["dll"])
+        self.cn0 = self.dllLockIndicator = float(kex["cn0"])
+        self.fllLockIndicator = float(kex["fll_lock"])
+        self.pllLockIndicator = float(kex["pll_lock"])
+        self.codeCounter += 1
+        self.codeSinceTOW += 1
+        self.carrierFrequency = float(rec["carrier_freq"])
+        self.codeFrequency = float(rec["code_freq"])
+        self.remainingCode = float(rec["rem_code"])
+        self.remainingCarrier = float(rec["rem_carrier"])
+        self.codeStep = self.codeFrequency / self.rfSignal.samplingFrequency
+        self.currentSample = (self.currentSample + self.track_requiredSamples) % self.rfBuffer.maxSize
+        self.track_requiredSamples = int(np.ceil((GPS_L1CA_CODE_SIZE_BITS - self.remainingCode) / self.codeStep))
+        # code lock / bit synchronisation as decided on the device; the other flags are host-side (decoding)
+        dev = int(kex["flags"]) & int(TrackingFlags.CODE_LOCK | TrackingFlags.BIT_SYNC)
+        if (dev & int(TrackingFlags.BIT_SYNC)) and not (self.trackFlags & TrackingFlags.BIT_SYNC):
+            self.correlatorsAccum[:] = self.correlatorsResults[:]
+            self.correlatorsAccumCounter = 1
+        keep = int(self.trackFlags) & ~int(TrackingFlags.CODE_LOCK | TrackingFlags.BIT_SYNC)
+        self.trackFlags = keep | dev
+        self.iPromptPrev = self.correlatorsResults[self.IDX_I_PROMPT]
+        self.qPromptPrev = self.correlatorsResults[self.IDX_Q_PROMPT]
+        self.loopLockState = LoopLockState(int(kex["lock_state"]))
+        return self.prepareResultsTracking()
 
     def runFrequencyDiscriminator(self, correlatorResults):
         """channel_l1ca_kaplan.py:623-631."""

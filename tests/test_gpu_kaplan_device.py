@@ -185,3 +185,6 @@ def test_receiver_with_the_kaplan_ini(tmp_path):
         for st in sorted(set(sb.astype(int)) - {1}):
             assert abs(int(np.argmax(sa == st)) - int(np.argmax(sb == st))) <= 3
         assert set(ra[0]) == set(rb[0])                                   # same columns
+        # run() batches the Kaplan channels on the device too (ChannelManager): the very same trajectory
+        for key in ("i_prompt", "carrier_frequency", "code_frequency", "cn0", "fll_lock", "pll_lock", "lock_state", "fll"):
+            assert [r[key] for r in ra[:n]] == [r[key] for r in rb[:n]], key
