@@ -5,11 +5,14 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
 
 One "step" = one pass of the hot path over one recording chunk: PCPS acquisition of 32 PRNs
-(+-5 kHz / 250 Hz, 1 ms x 10) on the first 10 ms, scalar hand-off, closed-loop E/P/L
-tracking of the 12 acquired channels over the whole chunk.  Weak scaling: every rank owns one
-recording (seed 1003 + rank); the only collective is the NCCL all-gather of the 24-byte peak
-records.  `value` is timed with the chunk resident in HBM; `e2e` goes through the public call
-(ColdStartPipeline.process_host) from pinned host memory, H2D and D2H inside the timed region.
+(+-5 kHz / 250 Hz, 1 ms x 10) on the first 10 ms, hand-off on the device, closed-loop E/P/L
+tracking of the 12 acquired channels over the whole chunk.  `--lanes` steps are kept in flight
+(ColdStartPool): the 12-channel tracking launch is a latency chain on part of the GPU, the
+acquisition of the next chunk runs beside it.  Weak scaling: every rank owns one recording
+(seed 1003 + rank); the only collective is the NCCL all-gather of the 24-byte peak records.
+`value` is timed with the chunks resident in HBM; `e2e` goes through the public calls
+(ColdStartPool.submit_host / result) from pinned host memory, H2D and D2H of every epoch record
+inside the timed region; `e2e.from_file` is the same workload from an IQ file (StreamingReceiver).
 """
 from __future__ import annotations
 
@@ -499,7 +502,6 @@ def main():
         hbm_peak, hbm_src = 6650.0, "fallback"
         if os.path.exists(peaks_file):
             hbm_peak, hbm_src = float(json.load(open(peaks_file))["hbm_gbs"]), "measured"
-        tf, clk = (np.zeros(1), np.zeros(1))
         import ctypes as C
         tfv, clkv = C.c_double(), C.c_double()
         L.check(lib.sydr_measure_fp32_peak(C.byref(tfv), C.byref(clkv)))
