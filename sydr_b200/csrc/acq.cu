@@ -224,7 +224,7 @@ __global__ void __launch_bounds__(P::T) acq_fwd_kernel(const AcqDev A, const voi
     // acquisition.py:34,42: freq = IF - bins[b], bins = arange(-range, range+1, step)
     // with shared spectra the transformed rows are the *global* rows 0 .. n_base-1, whatever Doppler range this
     // plan owns: every shard of a multi-GPU search then works from identical base spectra
-    const int grow = (HALVES == 1 && A.n_base > 0) ? row : A.bin_lo + row;
+    const int grow = (A.n_base > 0) ? row : A.bin_lo + row;
     const double fbin = -A.doppler_range + (double)grow * A.doppler_step;
     const double freq = A.inter_freq - fbin;
     const long long blk0 = (long long)blk * A.coh * NF;
@@ -356,14 +356,14 @@ __global__ void __launch_bounds__(P::T) acq_ifft_kernel(const AcqDev A, sydr_acq
 
     for (int blk = 0; blk < A.noncoh; ++blk) {
         // forward spectrum of this row: its own, or base row (row % n_base) read q = row / n_base bins lower
-        const int brow = (HALVES == 1 && A.n_base > 0) ? (A.bin_lo + row) % A.n_base : row;
-        const int qsh = (HALVES == 1 && A.n_base > 0) ? (A.bin_lo + row) / A.n_base : 0;
+        const int brow = (A.n_base > 0) ? (A.bin_lo + row) % A.n_base : row;
+        const int qsh = (A.n_base > 0) ? (A.bin_lo + row) / A.n_base : 0;
         const float2* __restrict__ Y = A.Y + ((size_t)brow * A.noncoh + blk) * NF;
         // swapped product z = swap(Y[f] * C[f]); Y of a split transform is stored [parity][m]
         auto zin = [&](int f) -> float2 {
             int fy = f - qsh;
             fy += (fy < 0) ? NF : 0;
-            const float2 y = (HALVES == 2) ? __ldg(Y + (size_t)(f & 1) * NH + (f >> 1)) : __ldg(Y + fy);
+            const float2 y = (HALVES == 2) ? __ldg(Y + (size_t)(fy & 1) * NH + (fy >> 1)) : __ldg(Y + fy);
             const float2 z = cmul(y, code_at(f));
             return make_float2(z.y, z.x);
         };
@@ -639,7 +639,7 @@ int launch_acq(sydr_acq_plan* pl, const void* d_iq, int dt, sydr_acq_row* d_rows
     {
         auto k = acq_fwd_kernel<P, HALVES>;
         SYDR_CUDA_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fft_bytes));
-        const int fwd_rows = (HALVES == 1 && A.n_base > 0) ? A.n_base : A.n_rows;
+        const int fwd_rows = (A.n_base > 0) ? A.n_base : A.n_rows;
         k<<<fwd_rows * A.noncoh * HALVES, P::T, fft_bytes, s>>>(A, d_iq, dt);
         count_launch();
         SYDR_CUDA_CHECK(cudaGetLastError());
@@ -809,7 +809,7 @@ int sydr_acq_plan_create(double fs, double inter_freq, double doppler_range, dou
     {
         const double g = (fs / (double)n_code) / doppler_step;
         const int G = (int)llround(g);
-        n_base = (shape.halves == 1 && G >= 1 && fabs(g - (double)G) < 1e-9) ? G : 0;    // global base rows, whatever the shard
+        n_base = (G >= 1 && fabs(g - (double)G) < 1e-9) ? G : 0;    // global base rows, whatever the shard
     }
     if (cudaMalloc(&pl->d_prns, sizeof(int) * n_prn) != cudaSuccess ||
         cudaMalloc(&pl->d_code_spec, sizeof(float2) * (size_t)n_prn * n_code) != cudaSuccess ||
