@@ -248,3 +248,29 @@ def test_streaming_append_matches_single_launch(golden):
         eng.launch(d_iq, iq_len=int(n * frac), append=True)
     parts = eng.fetch()[0]
     assert len(parts) == len(one) and parts.tobytes() == one.tobytes()
+
+
+def test_dense_instantiation_matches_latency_instantiation_at_the_headline_rate():
+    """The register-lean DENSE instantiation (ColdStartPool) and the latency instantiation walk the same
+    trajectory (int16, 25 MS/s, half-chip segment path, clusters of 8): identical epoch boundaries; the
+    correlator sums differ only by the FP32 partial-sum order of the two thread counts."""
+    from sydr_b200 import synth
+    from sydr_b200.engine import AcquisitionEngine, TrackingEngine, make_trk_states, to_device_iq
+    fs = 25e6
+    sc = synth.make_scenario(fs, 16, 0.12, (8, 17, 30), 61, 250.0)
+    d = to_device_iq(synth.generate_iq(sc))
+    acq = AcquisitionEngine(fs, 0.0, 5000, 250, 1, 10, [8, 17, 30])
+    peaks = acq.run(d)["peaks"]
+    chans = [dict(prn=int(p["prn"]), carrier_freq=acq.handoff(p)[0], start_sample=acq.handoff(p)[2], iq_len=d.numel() // 2)
+             for p in peaks]
+    acq.close()
+    out = []
+    for dense in (False, True):
+        eng = TrackingEngine(fs, make_trk_states(fs, chans), 130, dense=dense)
+        out.append(eng.run(d))
+    for a, b in zip(*out):
+        assert len(a) == len(b) >= 105
+        assert np.array_equal(a["start"], b["start"]) and np.array_equal(a["n"], b["n"])
+        assert corr_err(b["corr"], a["corr"]).max() <= 1e-5
+        assert np.abs(a["carrier_freq"] - b["carrier_freq"]).max() <= 1e-3
+        assert np.abs(a["code_freq"] - b["code_freq"]).max() <= 1e-3
