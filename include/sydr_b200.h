@@ -131,7 +131,9 @@ typedef struct {
 
 /* n_calls independent EPL evaluations; d_out receives 6 doubles each
  * [IE, QE, IP, QP, IL, QL].  d_iq must hold iq_len complex samples (16-byte aligned,
- * with at least 64 bytes of readable padding after the last sample). */
+ * with at least 64 bytes of readable padding after the last sample).  A call whose window
+ * [start, start+n) leaves the recording, whose n <= 0 or whose PRN has no code reads nothing
+ * and returns six NaNs (the reference's numpy slice would come up short and raise). */
 int sydr_epl_batch(const void* d_iq, int iq_dtype, long long iq_len, double fs,
                    const sydr_epl_args* d_args, int n_calls, double* d_out, void* stream);
 
@@ -143,7 +145,7 @@ typedef struct {
     int64_t cur;            /* currentSample: first sample of the next epoch (rec-relative) */
     int64_t n_req;          /* track_requiredSamples                                        */
     int64_t epochs_done;    /* epochs processed so far (all launches)                       */
-    int32_t prn;
+    int32_t prn;            /* 1..37; anything else aborts the channel (status SYDR_ERR_STATE) */
     int32_t status;         /* 0 ok; <0 = channel aborted (SYDR_ERR_STATE); >0 = idle slot:
                                the kernel leaves the channel untouched                      */
     double  carrier_freq;   /* carrierFrequency                                             */

@@ -773,6 +773,11 @@ __global__ void __launch_bounds__(256) epl_batch_kernel(const uint8_t* __restric
     __shared__ uint32_t segtab[NV > 0 ? kSegTab : 4];
     __shared__ int seg_q[3];
     const sydr_epl_args a = args[blockIdx.x];
+    // a call outside the recording or with no code for its PRN launches no loads: its six sums read NaN
+    if ((unsigned)(a.prn - 1) >= (unsigned)kMaxPrn || a.n <= 0 || a.start < 0 || a.start + a.n > iq_len) {
+        if (threadIdx.x < 6) out[(long long)blockIdx.x * 6 + threadIdx.x] = __longlong_as_double(0x7ff8000000000000LL);
+        return;
+    }
     if (threadIdx.x < kCodeWords) cb[threadIdx.x] = code_bits[(a.prn - 1) * kCodeWords + threadIdx.x];
     const long long a0 = a.start & ~(long long)(SPV - 1);     // 16-byte aligned window start
     const int lead = (int)(a.start - a0);
@@ -808,7 +813,6 @@ __global__ void __launch_bounds__(256) epl_batch_kernel(const uint8_t* __restric
     }
     const float tot = block_sum8(acc, red);
     if (threadIdx.x < 6) out[(long long)blockIdx.x * 6 + threadIdx.x] = (double)tot;
-    (void)iq_len;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1229,6 +1233,7 @@ trk_borre_kernel(const TrkParams P) {
         if (P.has_iq_base) sh.cfgs.iq_base = P.iq_base;
         sh.rec_base = P.append ? (int)sh.cfgs.epochs_done : (P.resume ? P.nepochs[ch] : 0);
         if (P.resume && sh.cfgs.status == kNeedGeneral) sh.cfgs.status = 0;
+        if ((unsigned)(sh.cfgs.prn - 1) >= (unsigned)kMaxPrn && sh.cfgs.status == 0) sh.cfgs.status = SYDR_ERR_STATE;   // no code for this PRN
         const sydr_trk_state& g = sh.cfgs;
         sh.sc.cur = g.cur; sh.sc.n_req = (int)g.n_req;
         sh.sc.code_freq = g.code_freq; sh.sc.code_step = g.code_step; sh.sc.rem_code = g.rem_code;
@@ -1251,7 +1256,7 @@ trk_borre_kernel(const TrkParams P) {
         fence_mbar_init();
     }
     __syncthreads();
-    if (tid < kCodeWords) sh.cb[tid] = P.code_bits[(sh.cfgs.prn - 1) * kCodeWords + tid];
+    if (tid < kCodeWords) sh.cb[tid] = P.code_bits[min(max(sh.cfgs.prn, 1), kMaxPrn) * kCodeWords - kCodeWords + tid];
     if (NV > 0 && sh.seg_ok) {
         __syncthreads();
         build_seg_table(sh.segtab, sh.cb, sh.seg_q);

@@ -289,7 +289,7 @@ class TrackingEngine:
         st = self.states()
         if (st["status"] < 0).any():
             bad = np.nonzero(st["status"] < 0)[0].tolist()
-            raise L.SydrError(f"tracking aborted on channels {bad} (NCO state left the supported range)")
+            raise L.SydrError(f"tracking failed (code -4): aborted on channels {bad} (NCO state left the supported range, or a PRN without a code)")
         return res
 
 
