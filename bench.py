@@ -144,12 +144,12 @@ def _cpu_trk_task(a):
     return time.perf_counter() - t0
 
 
-def cpu_baseline(host_iq_np, channels, chunk_samples, n_acq_prn=None, trk_epochs=40):
+def cpu_baseline(host_iq_np, channels, chunk_samples, n_acq_prn=None, trk_epochs=150):
     """Times a bounded sample of the step with one process per core (the reference's own
     process-per-channel model) and scales to the whole step."""
     import multiprocessing as mp
     cores = len(os.sched_getaffinity(0))
-    n_acq_prn = n_acq_prn or min(cores, 8)
+    n_acq_prn = n_acq_prn or len(SEARCH_PRNS)           # the whole 32-PRN search; the tracking leg is the sampled one
     n_dwell = int(FS * 1e-3) * ACQ["coh"] * ACQ["noncoh"]
     need = max(n_dwell, max(c["start_sample"] for c in channels) + (trk_epochs + 2) * int(FS * 1e-3))
     x = host_iq_np[:2 * need].astype(np.float64)
@@ -187,7 +187,8 @@ def run_reference(args, rank, world):
         return
     from sydr_b200 import synth
     chunk_samples = int(round(args.chunk_seconds * FS))
-    need_s = 0.010 + 0.050
+    ref_epochs = 100
+    need_s = 0.010 + (ref_epochs + 4) * 1e-3
     sc = synth.make_scenario(FS, NBITS, need_s + 0.02, synth.PRNS_12, 1003, 250.0)
     iq = synth.generate_iq(sc)
     n_code = int(FS * 1e-3)
@@ -198,7 +199,7 @@ def run_reference(args, rank, world):
         chans.append(dict(prn=s.prn, carrier_freq=fbin, start_sample=10 * n_code - n_code + code_idx + 1))
     vals = []
     for _ in range(args.warmup + args.steps):
-        vals.append(cpu_baseline(iq, chans, chunk_samples, trk_epochs=30))
+        vals.append(cpu_baseline(iq, chans, chunk_samples, trk_epochs=ref_epochs))
     vals = vals[args.warmup:]
     v = float(np.mean([b["value"] for b in vals]))
     base = vals[-1]
