@@ -1304,7 +1304,7 @@ trk_borre_kernel(const TrkParams P) {
     const long long cap64 = (long long)S * Q * C - SPV;
     const unsigned n_cap = (unsigned)(cap64 < 0 ? 0 : (cap64 > 0x7fffffffLL ? 0x7fffffffLL : cap64));
     const int epoch_cap = P.max_epochs - sh.rec_base;
-    const long long iq_len_reg = sh.cfgs.iq_len;
+    const long long iq_len_reg = sh.cfgs.iq_len < rec_alloc ? sh.cfgs.iq_len : rec_alloc;   // never past the allocation
     while (true) {
         // ---- (C, second half) publish the constants of epoch `epoch`
         if (warp == 0) {

@@ -108,3 +108,13 @@ def test_epl_batch_refuses_calls_outside_the_recording():
     out = epl_batch(iq, fs, args)
     assert np.isfinite(out[0]).all() and np.abs(out[0]).max() > 0
     assert np.isnan(out[1:]).all()            # window past the end, n = 0, PRN 0, PRN 38
+
+
+def test_tracking_stops_at_the_allocation_when_iq_len_overstates_it():
+    """A state whose iq_len claims more samples than the buffer holds is tracked to the end of the buffer only."""
+    from sydr_b200.engine import TrackingEngine, make_trk_states
+    fs = 4e6
+    iq = torch.randint(-20, 21, (2 * 40000,), dtype=torch.int8, device="cuda", generator=torch.Generator("cuda").manual_seed(7))
+    good = TrackingEngine(fs, make_trk_states(fs, [dict(prn=9, carrier_freq=0.0, start_sample=0, iq_len=40000)]), 64).run(iq)
+    over = TrackingEngine(fs, make_trk_states(fs, [dict(prn=9, carrier_freq=0.0, start_sample=0, iq_len=10 ** 9)]), 64).run(iq)
+    assert 9 <= len(over[0]) <= 10 and over[0].tobytes() == good[0][:len(over[0])].tobytes()
