@@ -124,10 +124,17 @@ class ClockSampler:
 
 # ----------------------------------------------------------------------------------------
 # CPU baseline: the NumPy restatement of the reference (oracle/) on the host cores.
-def _cpu_acq_task(a):
+# The samples reach the workers by fork inheritance (module global set before the pool is created), never
+# through a pipe; every worker times its own compute, and the wall clock around each leg is reported next to
+# the slowest and the summed worker times so that scheduling / IPC overhead is visible.
+_CPU_X = None                                  # complex128 samples of the recording
+
+
+def _cpu_acq_task(prn):
     from oracle import sydr_oracle as O
-    x, prn = a
     n = int(FS * 1e-3)
+    n_dwell = n * ACQ["coh"] * ACQ["noncoh"]
+    x = _CPU_X[:n_dwell]
     t0 = time.perf_counter()
     cmap = O.pcps(x[None, :], 0.0, FS, O.code_spectrum(prn, FS), ACQ["doppler_range"], ACQ["doppler_step"], n,
                   ACQ["coh"], ACQ["noncoh"])
@@ -137,37 +144,63 @@ def _cpu_acq_task(a):
 
 def _cpu_trk_task(a):
     from oracle import sydr_oracle as O
-    x, prn, carrier, start, epochs = a
+    prn, carrier, start, epochs = a
     tr = O.BorreTrackOracle(prn, FS, carrier, start)
     t0 = time.perf_counter()
-    tr.run(x, max_epochs=epochs)
-    return time.perf_counter() - t0
+    done = len(tr.run(_CPU_X, max_epochs=epochs))
+    return time.perf_counter() - t0, done
 
 
-def cpu_baseline(host_iq_np, channels, chunk_samples, n_acq_prn=None, trk_epochs=150):
-    """Times a bounded sample of the step with one process per core (the reference's own
-    process-per-channel model) and scales to the whole step."""
-    import multiprocessing as mp
-    cores = len(os.sched_getaffinity(0))
-    n_acq_prn = n_acq_prn or len(SEARCH_PRNS)           # the whole 32-PRN search; the tracking leg is the sampled one
+def cpu_prepare(host_iq_np, channels, trk_epochs):
+    """complex128 view of as much of the recording as `trk_epochs` epochs of every channel need."""
+    global _CPU_X
     n_dwell = int(FS * 1e-3) * ACQ["coh"] * ACQ["noncoh"]
     need = max(n_dwell, max(c["start_sample"] for c in channels) + (trk_epochs + 2) * int(FS * 1e-3))
-    x = host_iq_np[:2 * need].astype(np.float64)
-    x = x[0::2] + 1j * x[1::2]
-    ctx = mp.get_context("fork")
-    with ctx.Pool(min(cores, max(n_acq_prn, len(channels)))) as pool:
-        t0 = time.perf_counter()
-        pool.map(_cpu_acq_task, [(x[:n_dwell], p) for p in SEARCH_PRNS[:n_acq_prn]])
-        t_acq = time.perf_counter() - t0
-        t0 = time.perf_counter()
-        pool.map(_cpu_trk_task, [(x, c["prn"], c["carrier_freq"], c["start_sample"], trk_epochs) for c in channels])
-        t_trk = time.perf_counter() - t0
+    need = min(need, len(host_iq_np) // 2)
+    x = np.empty(need, dtype=np.complex128)
+    x.real = host_iq_np[0:2 * need:2]
+    x.imag = host_iq_np[1:2 * need:2]
+    _CPU_X = x
+
+
+def cpu_step(pool, channels, chunk_samples, trk_epochs):
+    """One pass of the hot path on the host cores: the whole 32-PRN acquisition + `trk_epochs` epochs of every
+    channel (the whole chunk when trk_epochs covers it), one worker process per core as the reference runs
+    one process per channel (sydr/channel/channel.py:121-160)."""
+    cores = len(os.sched_getaffinity(0))
+    t0 = time.perf_counter()
+    w_acq = pool.map(_cpu_acq_task, SEARCH_PRNS, chunksize=1)
+    t_acq = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    w_trk = pool.map(_cpu_trk_task, [(c["prn"], c["carrier_freq"], c["start_sample"], trk_epochs) for c in channels], chunksize=1)
+    t_trk = time.perf_counter() - t0
+    done = min(d for _, d in w_trk)
     chunk_epochs = chunk_samples / (FS * 1e-3)
-    est = t_acq * (len(SEARCH_PRNS) / n_acq_prn) + t_trk * (chunk_epochs / trk_epochs)
+    sampled = done < chunk_epochs - 12
+    scale = (chunk_epochs / done) if sampled else 1.0
+    est = t_acq + t_trk * scale
     return {"value": chunk_samples / est / 1e6, "unit": "Msamples/s", "cores": cores, "kind": "port",
-            "rtf": chunk_samples / FS / est,
-            "sample": f"{n_acq_prn} of 32 PRNs acquired ({t_acq:.2f} s) + {trk_epochs} of {chunk_epochs:.0f} epochs x "
-                      f"{len(channels)} channels tracked ({t_trk:.2f} s), NumPy oracle, one process per core, scaled to the step"}
+            "rtf": chunk_samples / FS / est, "sampled": bool(sampled), "timed_s": t_acq + t_trk, "step_s": est,
+            "acq": {"wall_s": t_acq, "worker_max_s": max(w_acq), "worker_sum_s": sum(w_acq), "prns": len(SEARCH_PRNS)},
+            "trk": {"wall_s": t_trk, "worker_max_s": max(t for t, _ in w_trk), "worker_sum_s": sum(t for t, _ in w_trk),
+                    "epochs": int(done), "of_epochs": int(chunk_epochs), "channels": len(channels), "scale": scale},
+            "sample": f"all 32 PRNs acquired ({t_acq:.2f} s wall) + {done} of {chunk_epochs:.0f} epochs x {len(channels)} channels "
+                      f"tracked ({t_trk:.2f} s wall{', scaled to the chunk' if sampled else ''}); NumPy oracle (oracle/sydr_oracle.py, "
+                      f"pinned to the reference's outputs), {min(cores, 32)} worker processes, samples inherited by fork"}
+
+
+def cpu_baseline(host_iq_np, channels, chunk_samples, trk_epochs=500):
+    """bench.py's cpu_baseline leg: a bounded sample (the whole acquisition + `trk_epochs` epochs per channel)."""
+    import multiprocessing as mp
+    global _CPU_X
+    cpu_prepare(host_iq_np, channels, trk_epochs)
+    cores = len(os.sched_getaffinity(0))
+    try:
+        with mp.get_context("fork").Pool(min(cores, len(SEARCH_PRNS))) as pool:
+            pool.map(_cpu_acq_task, SEARCH_PRNS[:min(cores, len(SEARCH_PRNS))], chunksize=1)     # workers import numpy / the oracle
+            return cpu_step(pool, channels, chunk_samples, trk_epochs)
+    finally:
+        _CPU_X = None
 
 
 # ----------------------------------------------------------------------------------------
@@ -183,31 +216,58 @@ def make_recording(rank, chunk_s, device):
 
 
 def run_reference(args, rank, world):
+    """--impl reference: the reference algorithm of the path on this box's host cores (the oracle port: the
+    Python reference itself cannot travel to the GPU box, and bench.py never reads /root/reference).  Same
+    recording, chunk and channel hand-off as the GPU arm; one step = the whole 32-PRN acquisition + the whole
+    chunk of 12-channel tracking when `steps + warmup` such steps fit --ref-budget-s, else a sample of >= 500
+    epochs per channel scaled to the chunk ("sampled": true)."""
     if rank != 0:
         return
+    import multiprocessing as mp
+    global _CPU_X
     from sydr_b200 import synth
     chunk_samples = int(round(args.chunk_seconds * FS))
-    ref_epochs = 100
-    need_s = 0.010 + (ref_epochs + 4) * 1e-3
-    sc = synth.make_scenario(FS, NBITS, need_s + 0.02, synth.PRNS_12, 1003, 250.0)
-    iq = synth.generate_iq(sc)
+    chunk_epochs = int(chunk_samples / (FS * 1e-3))
+    sc = synth.make_scenario(FS, NBITS, args.chunk_seconds, synth.PRNS_12, 1003, 250.0)
+    cores = len(os.sched_getaffinity(0))
+    with mp.get_context("fork").Pool(cores) as gen_pool:
+        iq = synth.generate_iq_parallel(sc, gen_pool)
     n_code = int(FS * 1e-3)
     chans = []
     for s in sc.sats:                      # hand-off state from the known truth (bin centre, code delay)
         fbin = round(s.doppler / 250.0) * 250.0
         code_idx = int(round((s.delay_chips / 1.023e6) * FS)) % n_code
         chans.append(dict(prn=s.prn, carrier_freq=fbin, start_sample=10 * n_code - n_code + code_idx + 1))
+    cpu_prepare(iq, chans, chunk_epochs)
+    del iq
     vals = []
-    for _ in range(args.warmup + args.steps):
-        vals.append(cpu_baseline(iq, chans, chunk_samples, trk_epochs=ref_epochs))
-    vals = vals[args.warmup:]
-    v = float(np.mean([b["value"] for b in vals]))
+    t_run = time.perf_counter()
+    with mp.get_context("fork").Pool(min(cores, len(SEARCH_PRNS))) as pool:
+        # calibration (untimed): worker start-up + how many epochs per step fit the budget
+        cal = cpu_step(pool, chans, chunk_samples, 100)
+        per_epoch = cal["trk"]["wall_s"] / cal["trk"]["epochs"]
+        per_step_budget = args.ref_budget_s / max(1, args.steps + args.warmup)
+        epochs = int((per_step_budget - cal["acq"]["wall_s"]) / per_epoch)
+        epochs = chunk_epochs if epochs >= chunk_epochs - 12 else max(500, epochs)
+        for _ in range(args.warmup):
+            cpu_step(pool, chans, chunk_samples, epochs)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            vals.append(cpu_step(pool, chans, chunk_samples, epochs))
+        timed = time.perf_counter() - t0
+    _CPU_X = None
+    step_s = float(np.mean([b["step_s"] for b in vals]))
+    v = chunk_samples / step_s / 1e6
     base = vals[-1]
     base["value"] = v
+    base["rtf"] = chunk_samples / FS / step_s
     line = {"impl": "reference", "metric": "cold acquisition (32 PRN) + 12-channel tracking throughput", "value": v,
             "unit": "Msamples/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": chunk_samples / v / 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic", "rtf": v * 1e6 / FS,
+            "ms_per_step": step_s * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "rtf": chunk_samples / FS / step_s,
+            "sampled": bool(base["sampled"]), "timed_s": timed, "run_s": time.perf_counter() - t_run,
+            "timed_note": "timed_s = wall clock of the K timed steps as executed; ms_per_step = the step scaled to the whole "
+                          "chunk (equal to timed_s / steps when sampled is false)",
             "config": workload_config(args, 1), "cpu_baseline": base,
             "e2e": {"value": v, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
@@ -366,6 +426,7 @@ def main():
     ap.add_argument("--stress-seconds", type=float, default=0.5)
     ap.add_argument("--ingest-seconds", type=float, default=6.0, help="length of the file-ingest measurement (0 = skip)")
     ap.add_argument("--ingest-chunk-seconds", type=float, default=1.0)
+    ap.add_argument("--ref-budget-s", type=float, default=150.0, help="--impl reference: wall budget of the whole run")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))

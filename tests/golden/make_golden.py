@@ -105,7 +105,7 @@ ACQ_CASES = {
     "cfg1": (4e6, 8, synth.PRNS_8, 1001, 5000, 100, 5, 10, synth.PRNS_8, None),
     "cfg2": (10e6, 8, synth.PRNS_8, 1002, 5000, 250, 1, 10, tuple(range(1, 33)), 19),
     "cfg3acq": (25e6, 16, synth.PRNS_12, 1003, 5000, 250, 1, 10, tuple(range(1, 33)), None),
-    "cfg4": (50e6, 8, synth.PRNS_8, 1004, 5000, 50, 1, 20, (3, 5, 31), None),
+    "cfg4": (50e6, 8, synth.PRNS_8, 1004, 5000, 50, 1, 20, tuple(synth.PRNS_8) + (5, 9, 16, 24), None),   # the 8 present + 4 absent
 }
 
 

@@ -1,0 +1,162 @@
+"""Parity of exactly what bench.py times ("Next round" item 1).
+
+(a) the headline chunk -- 2 s x 12 channels of 25 MS/s int16 IQ through ColdStartPool (five steps in
+    flight, DENSE tracking instantiation), closed loop on the device, against BorreTrackOracle:
+      * every epoch re-evaluated by the oracle from the kernel's own pre-epoch state (teacher forcing):
+        six correlator sums within 1e-4 of the prompt magnitude, loop outputs equal to 1e-9;
+      * the oracle run closed loop on its own: carrier / code frequency within 0.5 Hz and absolute code
+        phase within 1e-3 chip over the whole chunk (north_star tolerances);
+(b) the throughput instantiation (BASELINE configs[4] shape: several recordings x 12 channels in one
+    launch, one CTA per channel / one cluster per recording) with the same two comparisons and
+    status == 0 on every channel;
+(c) lives in test_gpu_acq.py (cfg4 golden widened to 8 present + 4 absent PRNs);
+(d) DENSE added to the closed-loop configurations checked against the reference channel's packets.
+
+Reference: sydr/channel/channel_l1ca_borre.py:333-451, sydr/dsp/tracking.py:92-186.
+The oracle legs run one process per channel (fork; the samples are inherited, not pickled).
+"""
+import multiprocessing as mp
+import os
+
+import numpy as np
+import pytest
+
+import helpers as H  # noqa: F401  (sys.path)
+
+pytestmark = pytest.mark.gpu
+
+FS = 25e6
+TOL_CORR = 1e-4
+TOL_HZ = 0.5
+TOL_CHIP = 1e-3
+
+_X = None           # complex samples of the recording under test, inherited by the forked workers
+
+
+def _oracle_channel(a):
+    """Teacher-forced and free-running oracle of one channel.  Returns the error figures."""
+    from oracle import sydr_oracle as O
+    prn, carrier, start, rec = a
+    x = _X
+    n_ep = len(rec)
+    # ---- teacher forced: the oracle computes the sums from the kernel's state, then takes the kernel's sums
+    tf = O.BorreTrackOracle(prn, FS, carrier, start)
+    e_corr = np.zeros(n_ep)
+    e_state = 0.0
+    bad_shape = 0
+    for k in range(n_ep):
+        if tf.cur != int(rec["start"][k]) or tf.n_req != int(rec["n"][k]):
+            bad_shape += 1
+            break
+        o = tf.step(x, corr_override=rec["corr"][k])
+        ref = np.asarray(o["corr"])
+        e_corr[k] = np.abs(rec["corr"][k] - ref).max() / np.hypot(ref[2], ref[3])
+        e_state = max(e_state,
+                      abs(rec["carrier_freq"][k] - o["carrier_frequency"]) / max(1.0, abs(o["carrier_frequency"])),
+                      abs(rec["code_freq"][k] - o["code_frequency"]) / o["code_frequency"],
+                      abs(rec["rem_code"][k] - tf.rem_code), abs(rec["rem_carrier"][k] - tf.rem_carrier))
+    # ---- free running: the oracle closes its own loops
+    fr = O.BorreTrackOracle(prn, FS, carrier, start)
+    d_car = d_code = d_phase = 0.0
+    for k in range(n_ep):
+        if fr.cur + fr.n_req > len(x):
+            break
+        o = fr.step(x)
+        d_car = max(d_car, abs(o["carrier_frequency"] - rec["carrier_freq"][k]))
+        d_code = max(d_code, abs(o["code_frequency"] - rec["code_freq"][k]))
+        # absolute code phase of the next epoch: end sample - remCode / codeStep, in chips
+        ours = (rec["start"][k] + rec["n"][k]) - rec["rem_code"][k] / (rec["code_freq"][k] / FS)
+        theirs = fr.cur - fr.rem_code / fr.code_step
+        d_phase = max(d_phase, abs(ours - theirs) * (1.023e6 / FS))
+    return dict(prn=prn, bad_shape=bad_shape, e_corr=float(e_corr.max()), e_corr_at=int(e_corr.argmax()),
+                e_state=float(e_state), d_car=d_car, d_code=d_code, d_phase=d_phase, epochs=n_ep)
+
+
+def check_against_oracle(x, chans, recs):
+    """x: complex samples per recording (list indexed by chans[i]['rec']) or one array."""
+    global _X
+    out = []
+    by_rec = {}
+    for c, r in zip(chans, recs):
+        by_rec.setdefault(c.get("rec", 0), []).append((c["prn"], c["carrier_freq"], c["start_sample"], r))
+    ctx = mp.get_context("fork")
+    for rec_i, tasks in by_rec.items():
+        _X = x[rec_i] if isinstance(x, list) else x
+        with ctx.Pool(min(len(tasks), len(os.sched_getaffinity(0)))) as pool:
+            out += pool.map(_oracle_channel, tasks)
+        _X = None
+    for o in out:
+        assert o["bad_shape"] == 0, f"PRN {o['prn']}: epoch boundaries differ from the reference arithmetic"
+        assert o["e_corr"] <= TOL_CORR, f"PRN {o['prn']}: correlators off by {o['e_corr']:.2e} at epoch {o['e_corr_at']}"
+        assert o["e_state"] <= 1e-9, f"PRN {o['prn']}: loop closure differs ({o['e_state']:.2e})"
+        assert o["d_car"] <= TOL_HZ and o["d_code"] <= TOL_HZ, (o["prn"], o["d_car"], o["d_code"])
+        assert o["d_phase"] <= TOL_CHIP, (o["prn"], o["d_phase"])
+    return out
+
+
+def to_c64(iq_int16: np.ndarray) -> np.ndarray:
+    """int16 I/Q pairs as complex64: exact (|v| < 2^24), half the memory of the reference's complex128."""
+    v = iq_int16.astype(np.float32)
+    return v.view(np.complex64)
+
+
+def test_headline_chunk_dense_pool_vs_oracle():
+    """bench.py's timed step: ColdStartPool(lanes=5) -> acquisition, device hand-off, DENSE 12-channel tracking
+    of a 2 s chunk; five steps in flight, every lane's records compared."""
+    import torch
+    from sydr_b200 import synth
+    from sydr_b200.pipeline import ColdStartPool
+    chunk_s, lanes = 2.0, 5
+    sc = synth.make_scenario(FS, 16, chunk_s, synth.PRNS_12, 1003, 250.0)
+    d = synth.generate_iq_torch(sc, device="cuda")
+    pool = ColdStartPool(lanes=lanes, fs=FS, nbits=16, search_prns=list(range(1, 33)), n_channels=12, max_seconds=chunk_s,
+                         doppler_range=5000.0, doppler_step=250.0, coh=1, noncoh=10)
+    assert all(p._dense for p in pool.lanes)
+    d_iq = pool.lanes[0].device_buffer(d.numel() // 2)
+    d_iq.copy_(d)
+    torch.cuda.synchronize()
+    tickets = [pool.submit_device(d_iq) for _ in range(lanes)]
+    outs = [pool.result(t, records=True, copy=True) for t in tickets]
+    pool.close()
+    first = outs[0]
+    assert [c["prn"] for c in first["channels"]] == list(synth.PRNS_12)
+    for o in outs[1:]:                                     # steps in flight beside each other: the same bits
+        assert o["peaks"].tobytes() == first["peaks"].tobytes()
+        for a, b in zip(o["epochs"], first["epochs"]):
+            assert a.tobytes() == b.tobytes()
+    assert min(len(e) for e in first["epochs"]) >= 1985
+    x = to_c64(d.cpu().numpy())
+    del d
+    res = check_against_oracle(x, first["channels"], first["epochs"])
+    print("headline chunk vs oracle:", {k: max(r[k] for r in res) for k in ("e_corr", "e_state", "d_car", "d_code", "d_phase")})
+
+
+@pytest.mark.parametrize("shape", ["cta_per_channel"])
+def test_throughput_instantiation_vs_oracle(shape):
+    """configs[4] shape: 3 recordings x 12 channels x 0.5 s in one launch of the throughput instantiation."""
+    import torch
+    from sydr_b200 import synth
+    from sydr_b200.engine import AcquisitionEngine, TrackingEngine, make_trk_states
+    n_rec, seconds = 3, 0.5
+    n = int(round(seconds * FS))
+    pad = 2048
+    buf = torch.zeros(n_rec * (2 * n + pad) + 4096, dtype=torch.int16, device="cuda")
+    acq = AcquisitionEngine(FS, 0.0, 5000.0, 250.0, 1, 10, list(synth.PRNS_12))
+    chans, xs = [], []
+    for r in range(n_rec):
+        sc = synth.make_scenario(FS, 16, seconds, synth.PRNS_12, 1005 + r, 250.0)
+        base = r * (2 * n + pad)
+        buf[base:base + 2 * n] = synth.generate_iq_torch(sc, device="cuda")
+        xs.append(to_c64(buf[base:base + 2 * n].cpu().numpy()))
+        for p in acq.run(buf[base:base + 2 * n])["peaks"]:
+            carrier, _, cur = acq.handoff(p)
+            chans.append(dict(prn=int(p["prn"]), carrier_freq=carrier, start_sample=cur, iq_base=base // 2, iq_len=n, rec=r))
+    acq.close()
+    st = make_trk_states(FS, chans)
+    eng = TrackingEngine(FS, st, int(seconds * 1000) + 8, cluster=1, threads=256, use_tma=False)   # the LEAN launch of bench.throughput_stress
+    eng.launch(buf)
+    recs = eng.fetch()
+    assert (eng.states()["status"] == 0).all()
+    assert min(len(r) for r in recs) >= 485
+    res = check_against_oracle(xs, chans, recs)
+    print("throughput launch vs oracle:", {k: max(r[k] for r in res) for k in ("e_corr", "e_state", "d_car", "d_code", "d_phase")})

@@ -132,11 +132,13 @@ def test_teacher_forced_epochs(golden, name):
 
 CONFIGS = [dict(cluster=1, threads=0, use_tma=True), dict(cluster=2, threads=0, use_tma=True),
            dict(cluster=4, threads=128, use_tma=True), dict(cluster=8, threads=0, use_tma=True),
-           dict(cluster=1, threads=256, use_tma=False), dict(cluster=8, threads=64, use_tma=False)]
+           dict(cluster=1, threads=256, use_tma=False), dict(cluster=8, threads=64, use_tma=False),
+           # the DENSE instantiation bench.py's timed region launches (ColdStartPool, several steps in flight)
+           dict(cluster=0, threads=0, use_tma=True, dense=True), dict(cluster=8, threads=160, use_tma=True, dense=True)]
 
 
 @pytest.mark.parametrize("name", ["fs4", "fs25"])
-@pytest.mark.parametrize("cfg", CONFIGS, ids=lambda c: f"S{c['cluster']}T{c['threads']}{'tma' if c['use_tma'] else 'ldg'}")
+@pytest.mark.parametrize("cfg", CONFIGS, ids=lambda c: f"S{c['cluster']}T{c['threads']}{'tma' if c['use_tma'] else 'ldg'}{'dense' if c.get('dense') else ''}")
 def test_closed_loop_vs_reference_channel(golden, name, cfg):
     from oracle import sydr_oracle as O
     from sydr_b200.engine import TrackingEngine, make_trk_states, to_device_iq
