@@ -196,6 +196,11 @@ typedef struct {
     int32_t use_iq_base;
     int32_t dense;          /* 1 = register-lean instantiation of the latency kernel (3 CTAs per SM): a few
                                per cent slower alone, denser when several launches share the GPU    */
+    int32_t kernel;         /* 0 = automatic; 1 = prefix-moment kernel (throughput shape: `group` channels of one
+                               recording per CTA share one pass over the samples; int16 IQ, Borre loops);
+                               2 = per-channel kernels only                                          */
+    int32_t group;          /* prefix-moment kernel: consecutive channels per CTA (1..4, same recording);
+                               0 = as many CTAs as fit one wave of the SMs                          */
 } sydr_trk_config;
 
 /* Closed-loop Borre tracking (runTracking, channel_l1ca_borre.py:333-451: EPL +

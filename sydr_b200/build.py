@@ -8,8 +8,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libsydr_b200.so")
-SOURCES = ["core.cu", "trk.cu", "acq.cu", "nav.cu", "legacy.cu"]
-HEADERS = ["common.cuh", "fft_radix.cuh", "fft_roots.inc", os.path.join("..", "..", "include", "sydr_b200.h")]
+SOURCES = ["core.cu", "trk.cu", "trkm.cu", "acq.cu", "nav.cu", "legacy.cu"]
+HEADERS = ["common.cuh", "trk_common.cuh", "fft_radix.cuh", "fft_roots.inc", os.path.join("..", "..", "include", "sydr_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
 

@@ -210,7 +210,7 @@ class TrackingEngine:
     """Closed-loop E/P/L tracking of many channels in one launch (K-TRK)."""
 
     def __init__(self, fs, states: np.ndarray, max_epochs: int, cluster=0, threads=0, use_tma=True, device=None,
-                 dense=False):
+                 dense=False, kernel=0, group=0):
         L.require_device()
         if device is not None:
             torch.cuda.set_device(device)
@@ -221,8 +221,10 @@ class TrackingEngine:
         self.max_epochs = int(max_epochs)
         st = np.ascontiguousarray(states)
         assert st.dtype == L.TRK_STATE_DTYPE
+        # kernel: 0 = automatic, 1 = prefix-moment kernel (throughput shape, `group` channels of a recording per CTA),
+        # 2 = per-channel kernels only
         self.cfg = L.TrkConfig(int(cluster), int(threads), 1 if use_tma else 0, 0, 0, min_tap_gap(st["spacing"]), 0, 0,
-                               1 if dense else 0)
+                               1 if dense else 0, int(kernel), int(group))
         self._states = torch.from_numpy(st.view(np.uint8).reshape(-1).copy()).to(self.device)
         self._out = torch.empty(self.n_ch * self.max_epochs * 128, dtype=torch.uint8, device=self.device)
         self._nep = torch.zeros(self.n_ch, dtype=torch.int32, device=self.device)

@@ -131,9 +131,15 @@ def test_headline_chunk_dense_pool_vs_oracle():
     print("headline chunk vs oracle:", {k: max(r[k] for r in res) for k in ("e_corr", "e_state", "d_car", "d_code", "d_phase")})
 
 
-@pytest.mark.parametrize("shape", ["cta_per_channel"])
+SHAPES = {"cta_per_channel": dict(cluster=1, threads=256, use_tma=False, kernel=2),      # LEAN instantiation of trk.cu
+          "moments_g3": dict(kernel=1, group=3), "moments_g4": dict(kernel=1, group=4), "moments_g1": dict(kernel=1, group=1)}
+
+
+@pytest.mark.parametrize("shape", list(SHAPES))
 def test_throughput_instantiation_vs_oracle(shape):
-    """configs[4] shape: 3 recordings x 12 channels x 0.5 s in one launch of the throughput instantiation."""
+    """configs[4] shape: 3 recordings x 12 channels x 0.5 s in one launch of the throughput kernels: the
+    prefix-moment kernel (trkm.cu, what bench.throughput_stress launches; 3 / 4 / 1 channels per CTA) and the
+    per-channel LEAN instantiation of trk.cu."""
     import torch
     from sydr_b200 import synth
     from sydr_b200.engine import AcquisitionEngine, TrackingEngine, make_trk_states
@@ -153,10 +159,10 @@ def test_throughput_instantiation_vs_oracle(shape):
             chans.append(dict(prn=int(p["prn"]), carrier_freq=carrier, start_sample=cur, iq_base=base // 2, iq_len=n, rec=r))
     acq.close()
     st = make_trk_states(FS, chans)
-    eng = TrackingEngine(FS, st, int(seconds * 1000) + 8, cluster=1, threads=256, use_tma=False)   # the LEAN launch of bench.throughput_stress
+    eng = TrackingEngine(FS, st, int(seconds * 1000) + 8, **SHAPES[shape])
     eng.launch(buf)
     recs = eng.fetch()
     assert (eng.states()["status"] == 0).all()
     assert min(len(r) for r in recs) >= 485
     res = check_against_oracle(xs, chans, recs)
-    print("throughput launch vs oracle:", {k: max(r[k] for r in res) for k in ("e_corr", "e_state", "d_car", "d_code", "d_phase")})
+    print(f"throughput launch ({shape}) vs oracle:", {k: max(r[k] for r in res) for k in ("e_corr", "e_state", "d_car", "d_code", "d_phase")})

@@ -134,13 +134,17 @@ CONFIGS = [dict(cluster=1, threads=0, use_tma=True), dict(cluster=2, threads=0, 
            dict(cluster=4, threads=128, use_tma=True), dict(cluster=8, threads=0, use_tma=True),
            dict(cluster=1, threads=256, use_tma=False), dict(cluster=8, threads=64, use_tma=False),
            # the DENSE instantiation bench.py's timed region launches (ColdStartPool, several steps in flight)
-           dict(cluster=0, threads=0, use_tma=True, dense=True), dict(cluster=8, threads=160, use_tma=True, dense=True)]
+           dict(cluster=0, threads=0, use_tma=True, dense=True), dict(cluster=8, threads=160, use_tma=True, dense=True),
+           # the prefix-moment kernel (trkm.cu; int16 IQ only: at fs4 / int8 it must hand every channel to the general kernel)
+           dict(cluster=0, threads=0, use_tma=True, kernel=1, group=1), dict(cluster=0, threads=0, use_tma=True, kernel=1, group=2)]
 
 
 @pytest.mark.parametrize("name", ["fs4", "fs25"])
-@pytest.mark.parametrize("cfg", CONFIGS, ids=lambda c: f"S{c['cluster']}T{c['threads']}{'tma' if c['use_tma'] else 'ldg'}{'dense' if c.get('dense') else ''}")
-def test_closed_loop_vs_reference_channel(golden, name, cfg):
+@pytest.mark.parametrize("cfg", CONFIGS, ids=lambda c: f"S{c['cluster']}T{c['threads']}{'tma' if c['use_tma'] else 'ldg'}{'dense' if c.get('dense') else ''}{('m%d' % c['group']) if c.get('kernel') == 1 else ''}")
+def test_closed_loop_vs_reference_channel(golden, name, cfg, trk_mode):
     from oracle import sydr_oracle as O
+    if cfg.get("kernel") == 1 and (name != "fs25" or trk_mode != 0):
+        pytest.skip("the prefix-moment kernel serves int16 IQ in the automatic mode")
     from sydr_b200.engine import TrackingEngine, make_trk_states, to_device_iq
     g = golden("loop.npz")
     meta, prns = g[f"{name}_meta"], g[f"{name}_prns"]
