@@ -196,11 +196,15 @@ typedef struct {
     int32_t use_iq_base;
     int32_t dense;          /* 1 = register-lean instantiation of the latency kernel (3 CTAs per SM): a few
                                per cent slower alone, denser when several launches share the GPU    */
-    int32_t kernel;         /* 0 = automatic; 1 = prefix-moment kernel (throughput shape: `group` channels of one
-                               recording per CTA share one pass over the samples; int16 IQ, Borre loops);
+    int32_t kernel;         /* 0 = automatic; 1 = prefix-moment kernel (throughput shape: the samples of a recording are
+                               turned into prefix moments once, every channel gathers from them; int16 IQ, Borre loops);
                                2 = per-channel kernels only                                          */
-    int32_t group;          /* prefix-moment kernel: consecutive channels per CTA (1..4, same recording);
-                               0 = as many CTAs as fit one wave of the SMs                          */
+    int32_t group;          /* prefix-moment kernel: correlating warps per channel (2, 4, 6, 8); 0 = default (4) */
+    int32_t rec_channels;   /* prefix-moment kernel: channel slots per recording -- channels
+                               [r*rec_channels, (r+1)*rec_channels) share recording r; 0 = all the channels are on
+                               one recording (a channel that is not on its slot's recording is served by the
+                               per-channel kernel)                                                   */
+    int32_t reserved;
 } sydr_trk_config;
 
 /* Closed-loop Borre tracking (runTracking, channel_l1ca_borre.py:333-451: EPL +

@@ -59,7 +59,7 @@ class TrkConfig(C.Structure):
     _fields_ = [("cluster", C.c_int32), ("threads", C.c_int32), ("use_tma", C.c_int32), ("append", C.c_int32),
                 ("iq_len", C.c_int64), ("min_tap_gap", C.c_double),
                 ("iq_base", C.c_int64), ("use_iq_base", C.c_int32), ("dense", C.c_int32),
-                ("kernel", C.c_int32), ("group", C.c_int32)]
+                ("kernel", C.c_int32), ("group", C.c_int32), ("rec_channels", C.c_int32), ("reserved", C.c_int32)]
 
 
 # numpy views of the same layouts (device buffers are torch uint8 tensors reinterpreted)

@@ -689,28 +689,28 @@ static int trk_run_impl(const void* d_iq, int iq_dtype, long long iq_alloc_sampl
     P.kout = d_kout;
     P.dense = cfg ? (cfg->dense != 0) : 0;
     cudaStream_t s = (cudaStream_t)stream;
-    // Prefix-moment kernel (trkm.cu): the throughput shape for int16 IQ -- chosen where the LEAN instantiation used to
-    // be (channels outnumber the SMs' latency-mode capacity), or explicitly with cfg.kernel = 1; cfg.kernel = 2 keeps the
-    // per-channel kernels.  Channels it cannot serve stop with kNeedGeneral and continue in the general launch below.
+    // Prefix-moment kernel (trkm.cu): the per-sample work done once per recording (int16 IQ) -- only on request
+    // (cfg.kernel = 1): measured slower than the LEAN instantiation on this GPU, so the automatic
+    // choice stays with the per-channel kernels.  Channels it cannot serve stop with kNeedGeneral and continue in the
+    // general launch below.
     const int kernel_sel = cfg ? cfg->kernel : 0;
     SYDR_REQUIRE(kernel_sel >= 0 && kernel_sel <= 2, SYDR_ERR_ARG, "cfg.kernel must be 0, 1 or 2 (got %d)", kernel_sel);
-    const bool moments_ok = iq_dtype == SYDR_IQ_I16 && g_trk_mode == 0 && d_kstates == nullptr && g_trk_prof == nullptr;
+    const bool moments_ok = iq_dtype == SYDR_IQ_I16 && g_trk_mode == 0 && d_kstates == nullptr && (g_trk_prof == nullptr || kernel_sel == 1);
     SYDR_REQUIRE(kernel_sel != 1 || moments_ok, SYDR_ERR_UNSUPPORTED,
                  "cfg.kernel = 1 (prefix-moment kernel) needs int16 IQ, the Borre loops and trk mode 0");
-    const bool moments = moments_ok && (kernel_sel == 1 || (kernel_sel == 0 && lean));
+    bool moments = moments_ok && kernel_sel == 1;
     if (moments) {
-        int group = cfg ? cfg->group : 0;
-        if (group <= 0) {
-            // as many CTAs as fit one wave of the SMs: 384 channels -> 3 per CTA (128 CTAs), 444 -> 3 (148)
-            group = 1;
-            while (group < 4 && (n_channels + group - 1) / group > 148) ++group;
-        }
         TrkParams PL = P;
         PL.use_tma = 1;
-        set_scale(PL, 4);
-        const int rc2 = launch_trkm(PL, n_channels, group, s);
-        if (rc2 != SYDR_OK) return rc2;
+        const int cw = cfg ? cfg->group : 0;
+        set_scale(PL, cw > 0 ? cw : 2);
+        const int rc2 = launch_trkm(PL, n_channels, cfg ? cfg->rec_channels : 0, cw, s);
+        if (rc2 == SYDR_ERR_UNSUPPORTED && kernel_sel == 0) moments = false;       // more channels on one recording than the device holds: per-channel kernels
+        else if (rc2 != SYDR_OK) return rc2;
+    }
+    if (moments) {
         P.resume = 1;
+        P.prof = nullptr;                    // (the counters of a diagnostics run belong to the prefix-moment kernel)
         if (auto_shape) threads = kTrkMaxThreads;
     } else if (lean) {
         TrkParams PL = P;

@@ -206,6 +206,17 @@ def min_tap_gap(spacing: np.ndarray) -> float:
     return gap
 
 
+def _rec_channels(iq_base: np.ndarray) -> int:
+    """Channel slots per recording when the channels come recording by recording in runs of equal length
+    (the prefix-moment kernel then keeps every CTA on one recording); 0 otherwise."""
+    b = np.asarray(iq_base)
+    if len(b) == 0:
+        return 0
+    cuts = np.flatnonzero(b[1:] != b[:-1]) + 1
+    runs = np.diff(np.concatenate(([0], cuts, [len(b)])))
+    return int(runs[0]) if len(runs) > 1 and (runs == runs[0]).all() else 0
+
+
 class TrackingEngine:
     """Closed-loop E/P/L tracking of many channels in one launch (K-TRK)."""
 
@@ -224,7 +235,7 @@ class TrackingEngine:
         # kernel: 0 = automatic, 1 = prefix-moment kernel (throughput shape, `group` channels of a recording per CTA),
         # 2 = per-channel kernels only
         self.cfg = L.TrkConfig(int(cluster), int(threads), 1 if use_tma else 0, 0, 0, min_tap_gap(st["spacing"]), 0, 0,
-                               1 if dense else 0, int(kernel), int(group))
+                               1 if dense else 0, int(kernel), int(group), _rec_channels(st["iq_base"]), 0)
         self._states = torch.from_numpy(st.view(np.uint8).reshape(-1).copy()).to(self.device)
         self._out = torch.empty(self.n_ch * self.max_epochs * 128, dtype=torch.uint8, device=self.device)
         self._nep = torch.zeros(self.n_ch, dtype=torch.int32, device=self.device)
@@ -248,6 +259,7 @@ class TrackingEngine:
         st = np.ascontiguousarray(states)
         assert st.dtype == L.TRK_STATE_DTYPE and len(st) == self.n_ch
         self.cfg.min_tap_gap = min_tap_gap(st["spacing"])
+        self.cfg.rec_channels = _rec_channels(st["iq_base"])
         self._states.copy_(torch.from_numpy(st.view(np.uint8).reshape(-1)))
 
     def launch(self, iq_dev: torch.Tensor, stream=None, iq_len: int = 0, append: bool = False, iq_base=None):

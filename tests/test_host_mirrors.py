@@ -120,7 +120,8 @@ def test_new_struct_layouts():
     import ctypes as C
     from sydr_b200 import _lib as L
     assert L.NAV_STATE_DTYPE.itemsize == 48 and L.NAV_STATE_DTYPE.fields["nav_count"][1] == 40
-    assert C.sizeof(L.TrkConfig) == 48 and L.TrkConfig.iq_base.offset == 32 and L.TrkConfig.use_iq_base.offset == 40
+    assert C.sizeof(L.TrkConfig) == 64 and L.TrkConfig.iq_base.offset == 32 and L.TrkConfig.use_iq_base.offset == 40
+    assert L.TrkConfig.kernel.offset == 48 and L.TrkConfig.group.offset == 52 and L.TrkConfig.rec_channels.offset == 56
 
 
 def _borre_channel():

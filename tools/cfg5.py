@@ -41,14 +41,24 @@ def main():
     n_ch = len(chans)
     max_ep = int(dur * 1000) + 8
     L.load().sydr_trk_profile_buffer(None)
-    shapes = [(1, 0, 1), (1, 0, 0), (1, 512, 0), (1, 416, 0), (1, 320, 0), (1, 256, 0), (2, 0, 1), (2, 320, 0)]
+    import os
+    prof = None
+    if os.environ.get("TRKM_PROF"):           # cycle counters of the prefix-moment kernel (diagnostics instantiation)
+        prof = torch.zeros(n_ch * 16, dtype=torch.int64, device="cuda")
+        L.load().sydr_trk_profile_buffer(prof.data_ptr())
+    # (cluster, threads, tma[, kernel, group]): kernel 1 = prefix-moment kernel (trkm.cu; group = correlating warps per channel),
+    # 2 = per-channel kernels (trk.cu)
+    shapes = [(0, 0, 1, 1, 4), (0, 0, 1, 1, 8), (0, 0, 1, 1, 2), (1, 256, 0, 2, 0)]
     if len(sys.argv) > 3:
         shapes = [tuple(int(v) for v in a.split(",")) for a in sys.argv[3:]]
-    for cluster, threads, tma in shapes:
+    for shp in shapes:
+        cluster, threads, tma = shp[:3]
+        kernel, group = (shp[3], shp[4]) if len(shp) >= 5 else (2, 0)
         ts = []
         try:
             for rep in range(3):
-                eng = TrackingEngine(fs, make_trk_states(fs, chans), max_ep, cluster=cluster, threads=threads, use_tma=bool(tma))
+                eng = TrackingEngine(fs, make_trk_states(fs, chans), max_ep, cluster=cluster, threads=threads, use_tma=bool(tma),
+                                     kernel=kernel, group=group)
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record(); eng.launch(buf); e1.record(); torch.cuda.synchronize()
                 ts.append(e0.elapsed_time(e1))
@@ -56,12 +66,21 @@ def main():
             print(f"S={cluster} T={threads} tma={tma}: {e}")
             continue
         res = eng.fetch()
+        if prof is not None and kernel == 1:
+            pc = prof.cpu().numpy().reshape(-1, 16).astype(float)
+            ep = np.maximum(pc[:, 7], 1)
+            print("   consumer warp 2, cycles per epoch (mean / min / max over channels): " + "  ".join(
+                f"{nm} {(pc[:, i] / ep).mean():.0f}/{(pc[:, i] / ep).min():.0f}/{(pc[:, i] / ep).max():.0f}"
+                for i, nm in ((0, "total"), (1, "top+gather issue"), (2, "e0 valid"), (13, "math"), (14, "amb"), (15, "n_amb"), (3, "barrier A"), (4, "correlate"), (5, "sleeps"), (6, "rounds"))))
+            nb = np.maximum(pc[:, 10], 1)
+            print("   producer warp, cycles per block: " + "  ".join(f"{nm} {(pc[:, i] / nb).mean():.0f}/{(pc[:, i] / nb).min():.0f}/{(pc[:, i] / nb).max():.0f}"
+                  for i, nm in ((9, "ring wait"), (11, "load+scan"), (12, "store+fence"))) + f"  blocks per warp {pc[:, 10].mean():.0f}  total cycles {pc[:, 8].mean():.3g}")
         nep = np.array([len(r) for r in res])
         err = np.array([abs(r["carrier_freq"][-1] - t) for r, t in zip(res, truth)])
         ms = min(ts)
         samples = float(sum(r["n"].sum() for r in res))
         tflops = 31.0 * samples / (ms * 1e-3) / 1e12
-        print(f"R={n_rec} ch={n_ch} S={cluster} T={threads:3d} tma={tma}: {ms:8.2f} ms  {ms * 1e3 / nep.mean():7.2f} us/epoch(all ch)  "
+        print(f"R={n_rec} ch={n_ch} S={cluster} T={threads:3d} tma={tma} kernel={kernel} group={group}: {ms:8.2f} ms  {ms * 1e3 / nep.mean():7.2f} us/epoch(all ch)  "
               f"RTF {dur * 1e3 / ms:6.1f}  {samples / (ms * 1e-3) / 1e9:7.1f} Gsample-ch/s  {tflops:6.2f} TFLOP/s alg  "
               f"epochs {nep.min()}..{nep.max()}  max|df| {err.max():.2f} Hz", flush=True)
 

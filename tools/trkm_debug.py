@@ -9,7 +9,7 @@ from sydr_b200.engine import AcquisitionEngine, TrackingEngine, make_trk_states
 
 FS = 25e6
 n_rec, seconds = int(sys.argv[1]) if len(sys.argv) > 1 else 3, float(sys.argv[2]) if len(sys.argv) > 2 else 0.5
-group = int(sys.argv[3]) if len(sys.argv) > 3 else 3
+group = int(sys.argv[3]) if len(sys.argv) > 3 else 4
 n = int(round(seconds * FS)); pad = 2048
 buf = torch.zeros(n_rec * (2 * n + pad) + 4096, dtype=torch.int16, device="cuda")
 acq = AcquisitionEngine(FS, 0.0, 5000.0, 250.0, 1, 10, list(synth.PRNS_12))
@@ -52,6 +52,8 @@ from fractions import Fraction as F
 from sydr_b200.synth import ca_code_pm1
 L.load().sydr_trkm_debug(int(os.environ.get("TRKM_DEBUG", "0")))
 m.reset(st); m.launch(buf); b = m.fetch()
+if os.environ.get("TRKM_CHECK_REF"):          # check the per-channel kernel's records instead
+    b = a
 hbuf = buf.cpu().numpy()
 events = 0
 for c, rb in enumerate(b):
