@@ -46,6 +46,7 @@ extern "C" {
 /* ------------------------------------------------------------------ library --------- */
 int         sydr_abi_version(void);
 const char* sydr_last_error(void);
+void        sydr_clear_error(void);             /* the legacy void entry points (section 9) report through the message only */
 int         sydr_device_count(void);            /* 0 when no CUDA device is usable      */
 int         sydr_set_device(int device);
 /* Measured FP32 FMA-chain peak of the current device (roofline denominator). */

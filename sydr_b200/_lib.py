@@ -104,6 +104,7 @@ _dp, _ip, _llp = C.POINTER(C.c_double), C.POINTER(C.c_int), C.POINTER(C.c_longlo
 SIGNATURES = {
     "sydr_abi_version": (_i, []),
     "sydr_last_error": (C.c_char_p, []),
+    "sydr_clear_error": (None, []),
     "sydr_device_count": (_i, []),
     "sydr_set_device": (_i, [_i]),
     "sydr_measure_fp32_peak": (_i, [_dp, _dp]),

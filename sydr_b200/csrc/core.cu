@@ -146,6 +146,7 @@ extern "C" {
 
 int sydr_abi_version(void) { return SYDR_ABI_VERSION; }
 const char* sydr_last_error(void) { return g_err; }
+void sydr_clear_error(void) { g_err[0] = '\0'; }
 long long sydr_launch_count(void) { return g_launches.load(); }
 void sydr_reset_launch_count(void) { g_launches = 0; }
 
