@@ -390,6 +390,71 @@ def cufft_comparison(dev, d_iq, ours_peaks, reps=5):
             "peaks_equal_k_acq": bool(same)}
 
 
+def acq_split_bench(dev, rank, world, steps=10, warmup=3):
+    """BASELINE.json configs[3] -- 50 MS/s, 32 PRNs, 50 Hz bins (201 rows), 20 ms non-coherent -- with the (PRN, Doppler) cells
+    split over the ranks by shard.plan_acquisition and ONE real collective per sweep: the NCCL all-gather of the 24-byte peak
+    records.  Every rank holds the same 20 ms recording (broadcast from rank 0); strong scaling (the sweep is fixed).  The
+    gathered table must be byte-identical on every rank and to the table one GPU computes alone (rank 0 runs the whole
+    sweep as well).  sydr/dsp/acquisition.py:41 is the bin loop being split."""
+    import torch
+    import torch.distributed as dist
+    from sydr_b200 import synth
+    from sydr_b200.engine import AcquisitionEngine
+    from sydr_b200.shard import ShardedAcquisition
+    fs, dr, ds, coh, noncoh = 50e6, 5000.0, 50.0, 1, 20
+    sc = synth.baseline_scenario(4)
+    d_iq = synth.generate_iq_torch(sc, device=dev)
+    if world > 1:
+        dist.broadcast(d_iq, src=0)
+    sh = ShardedAcquisition(fs, 0.0, dr, ds, coh, noncoh, SEARCH_PRNS, rank, world, device=dev)
+    for _ in range(warmup):
+        table = sh.run(d_iq)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        table = sh.run(d_iq)                     # launch, all-gather, table on the host
+    e1.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1) / steps], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t[0])
+    # byte-identity: every rank's table against rank 0's, and rank 0's against the sweep done by one GPU alone
+    mine = torch.from_numpy(table.view(np.uint8).copy()).to(dev)
+    ref = mine.clone()
+    if world > 1:
+        dist.broadcast(ref, src=0)
+    same = torch.tensor([1 if torch.equal(mine, ref) else 0], device=dev)
+    alone_ms, same_alone = None, True
+    if rank == 0:
+        eng = AcquisitionEngine(fs, 0.0, dr, ds, coh, noncoh, SEARCH_PRNS, device=dev)
+        full = eng.run(d_iq)["peaks"]
+        ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ea.record(); eng.launch(d_iq); eb.record(); torch.cuda.synchronize()
+        alone_ms = ea.elapsed_time(eb)
+        eng.close()
+        same_alone = full.tobytes() == table.tobytes()
+    if world > 1:
+        dist.all_reduce(same, op=dist.ReduceOp.MIN)
+    sh.close()
+    n_dwell = int(fs * 1e-3) * coh * noncoh
+    bins = 201
+    flop = len(SEARCH_PRNS) * bins * coh * noncoh * f_acq(int(fs * 1e-3))
+    found = sorted(int(p["prn"]) for p in table if p["ratio"] > 1.5)
+    if not (bool(same.item()) and same_alone) or found != sorted(s.prn for s in sc.sats):
+        raise SystemExit(f"acquisition split: tables differ (ranks equal {bool(same.item())}, equal to one GPU {same_alone}), found {found}")
+    return {"workload": "configs[3]: 50 MS/s int8, 32 PRNs x 201 Doppler rows (50 Hz) x 20 ms non-coherent, cells split by "
+                        f"{sh.shard.mode} over {world} GPU(s), NCCL all-gather of the peak records (768 B)",
+            "ms_per_sweep": ms, "sweeps_per_s": 1e3 / ms, "Msamples_per_s": n_dwell / (ms * 1e-3) / 1e6, "n_gpus": world,
+            "scaling": "strong", "one_gpu_alone_ms": alone_ms, "tflops_algorithmic": flop / (ms * 1e-3) / 1e12,
+            "table_identical_on_all_ranks": bool(same.item()), "table_identical_to_one_gpu": bool(same_alone),
+            "prns_found": found, "timing": "CUDA events around K sweeps (launch + all-gather + table to the host), max over ranks"}
+
+
 def file_ingest(dev, seconds, chunk_seconds, reader_threads=8, reps=3):
     """the same workload from an IQ *file* (cfg3 format) through StreamingReceiver:
     threaded reads into pinned buffers, H2D on a copy stream, sliding device windows, acquisition once,
@@ -484,6 +549,9 @@ def main():
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200")
+    ap.add_argument("--workload", default="cfg3", choices=["cfg3", "cfg4"],
+                    help="cfg3 (default): cold start + 12-channel tracking of a 60 s recording per GPU; cfg4: the 50 MS/s "
+                         "fine acquisition sweep split over the GPUs")
     ap.add_argument("--chunk-seconds", type=float, default=60.0,
                     help="length of the recording a step processes (BASELINE.json configs[2]: 60 s)")
     ap.add_argument("--lanes", type=int, default=5, help="steps in flight per GPU (ColdStartPool)")
@@ -492,6 +560,7 @@ def main():
     ap.add_argument("--no-tma", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-kaplan", action="store_true", help="skip the Kaplan loop-closure measurement")
+    ap.add_argument("--no-gather", action="store_true", help="diagnostics: N > 1 without the peak-table all-gather")
     ap.add_argument("--no-cufft", action="store_true", help="skip the cuFFT timed comparison of the acquisition sweep")
     ap.add_argument("--stress-recordings", type=int, default=32, help="recordings of the cfg-5 throughput measurement (0 = skip)")
     ap.add_argument("--stress-seconds", type=float, default=0.5)
@@ -516,6 +585,18 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     lib = L.load()
     L.check(lib.sydr_set_device(local))
+    if args.workload == "cfg4":
+        lib.sydr_reset_launch_count()
+        r = acq_split_bench(dev, rank, world, steps=args.steps, warmup=args.warmup)
+        if rank == 0:
+            print(json.dumps({"metric": "fine acquisition sweep (32 PRN x 201 bins x 20 ms @ 50 MS/s) throughput", "value": r["Msamples_per_s"],
+                              "unit": "Msamples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                              "ms_per_step": r["ms_per_sweep"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                              "dtype": "f32", "data": "synthetic", "config": {"workload": r["workload"]},
+                              "gpu_launches": int(lib.sydr_launch_count()), "acq_split": r}))
+        if world > 1:
+            dist.destroy_process_group()
+        return
 
     sc, host = make_recording(rank, args.chunk_seconds, dev)
     chunk_samples = host.numel() // 2
@@ -527,25 +608,31 @@ def main():
     pipe = pool.lanes[0]
     d_iq = pipe.upload(host)
     torch.cuda.synchronize()
-    gathered = torch.empty(world * len(SEARCH_PRNS) * 24, dtype=torch.uint8, device=dev) if world > 1 else None
-
+    # The acquisition peak tables (768 B per step and rank) are all-gathered over NCCL in ONE collective per K steps: every
+    # step snapshots its table on the lane's side stream into a history buffer, the collective follows the last step.
+    # (One collective per step, enqueued while five tracking launches fill the SMs, stalled the enqueueing host thread
+    # for ~6 ms per step on 2 GPUs: profiles/r2/bench_2gpu_allgather_per_step.json.)
+    PEAK_BYTES = len(SEARCH_PRNS) * 24
     comm = torch.cuda.Stream(device=dev) if world > 1 else None
-    gathered_l = [torch.empty_like(gathered) for _ in range(args.lanes)] if world > 1 else None
-    peaks_l = [torch.empty(len(SEARCH_PRNS) * 24, dtype=torch.uint8, device=dev) for _ in range(args.lanes)] if world > 1 else None
+    peaks_hist = torch.zeros(max(args.steps, args.warmup, 2) * PEAK_BYTES, dtype=torch.uint8, device=dev) if world > 1 else None
+    gathered = torch.empty(world * peaks_hist.numel(), dtype=torch.uint8, device=dev) if world > 1 else None
+    step_no = [0]
 
-    def gather_peaks(ticket):                           # the acquisition peak table, 768 B per rank
-        if world > 1:
-            # behind the acquisition (a snapshot of the peak table taken on the lane's side stream), on a
-            # communication stream of its own: a slow peer delays neither this rank's tracking nor its host
-            lane = pool.lane_index(ticket)
-            side = pool.peak_stream(lane)
-            with torch.cuda.stream(side):
-                peaks_l[lane].copy_(pool.lanes[lane].acq.peaks_device(), non_blocking=True)
-                ev = torch.cuda.Event()
-                ev.record(side)
-            comm.wait_event(ev)
+    def peaks_slot():
+        """Where this step's peak table goes (None on one GPU): the pipeline copies it there in stream order, right
+        behind the acquisition."""
+        if world == 1 or args.no_gather:
+            return None
+        k = step_no[0] % (peaks_hist.numel() // PEAK_BYTES)
+        step_no[0] += 1
+        return peaks_hist[k * PEAK_BYTES:(k + 1) * PEAK_BYTES]
+
+    def gather_peaks():
+        if world > 1 and not args.no_gather:
+            for lane in range(args.lanes):
+                comm.wait_stream(pool.stream(lane))
             with torch.cuda.stream(comm):
-                dist.all_gather_into_tensor(gathered_l[lane], peaks_l[lane])
+                dist.all_gather_into_tensor(gathered, peaks_hist)
 
     def run_steps(n, submit, records, marks_out=None):
         """n steps with at most `lanes` in flight; results collected in order."""
@@ -555,10 +642,10 @@ def main():
                 pool.result(tickets.pop(0), records=records)
             marks = [] if marks_out is not None else None
             t = submit(marks)
-            gather_peaks(t)
             tickets.append(t)
             if marks_out is not None:
                 marks_out.append(marks)
+        gather_peaks()
         while tickets:
             pool.result(tickets.pop(0), records=records)
 
@@ -584,7 +671,7 @@ def main():
     d2h_bytes = len(SEARCH_PRNS) * 24 + sum(e.nbytes for e in out["epochs"]) + 4 * len(out["epochs"])
 
     # ---- warm-up, then K steps resident in HBM
-    run_steps(args.warmup, lambda m: pool.submit_device(d_iq, m), False)
+    run_steps(args.warmup, lambda m: pool.submit_device(d_iq, m, peaks_slot()), False)
     sampler = ClockSampler(local)
     sampler.start()                                     # (NVML start-up takes milliseconds: before the barrier)
     lib.sydr_reset_launch_count()
@@ -592,7 +679,7 @@ def main():
     k_ev = []
     barrier()                                           # every rank enters the timed region together
     ev[0].record()
-    run_steps(args.steps, lambda m: pool.submit_device(d_iq, m), False, k_ev)
+    run_steps(args.steps, lambda m: pool.submit_device(d_iq, m, peaks_slot()), False, k_ev)
     barrier()
     ev[1].record()
     torch.cuda.synchronize()
@@ -629,16 +716,36 @@ def main():
             kap = {"error": f"{type(exc).__name__}: {exc}"}
 
     # ---- K steps end to end from pinned host memory
-    run_steps(2, lambda m: pool.submit_host(host), True)
+    run_steps(2, lambda m: pool.submit_host(host, peaks_out=peaks_slot()), True)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    run_steps(args.steps, lambda m: pool.submit_host(host), True)
+    run_steps(args.steps, lambda m: pool.submit_host(host, peaks_out=peaks_slot()), True)
     barrier()
     e1.record()
     torch.cuda.synchronize()
     ms_e2e = e0.elapsed_time(e1)
     clocks = sampler.stop()
+
+    # ---- the gathered peak tables of the last steps are read: every rank's 32 records, 12 satellites found on each
+    gathered_ok = None
+    if world > 1 and not args.no_gather:
+        comm.synchronize()
+        from sydr_b200 import _lib as _L
+        n_hist = peaks_hist.numel() // PEAK_BYTES
+        g = gathered.cpu().numpy().view(_L.ACQ_PEAK_DTYPE).reshape(world, n_hist, len(SEARCH_PRNS))[:, :min(args.steps, n_hist)]
+        gathered_ok = bool(all(int((g[r, k]["ratio"] > 1.5).sum()) == N_CHANNELS and (g[r, k]["prn"] == np.array(SEARCH_PRNS)).all()
+                               for r in range(world) for k in range(g.shape[1])))
+        if not gathered_ok:
+            raise SystemExit(f"rank {rank}: the all-gathered peak tables are not the ranks' acquisition results")
+
+    # ---- the other sharded path: configs[3]'s acquisition cells split over the ranks, real all-gather
+    acq_split = None
+    if world > 1:
+        try:
+            acq_split = acq_split_bench(dev, rank, world)
+        except (Exception, SystemExit) as exc:
+            acq_split = {"error": f"{type(exc).__name__}: {exc}"}
 
     t = torch.tensor([ms_dev, ms_e2e], dtype=torch.float64, device=dev)
     if world > 1:
@@ -723,6 +830,9 @@ def main():
                 "e2e": {"value": e2e, "unit": "Msamples/s", "rtf": e2e * 1e6 / FS / world,
                         "h2d_bytes_per_step": int(host.numel() * host.element_size()), "d2h_bytes_per_step": int(d2h_bytes)},
                 "gpu_launches": launches, "roofline": roofline}
+        if acq_split is not None:
+            line["acq_split"] = acq_split
+            line["gathered_peak_tables_ok"] = gathered_ok
         if world == 1 and args.ingest_seconds > 0:
             try:
                 line["e2e"]["from_file"] = file_ingest(dev, args.ingest_seconds, args.ingest_chunk_seconds)

@@ -127,7 +127,7 @@ class ColdStartPipeline:
             chans.append(dict(prn=int(peaks["prn"][i]), carrier_freq=carrier, start_sample=cur, iq_len=n_samples))
         return chans
 
-    def enqueue_device(self, d_iq: torch.Tensor, marks: list | None = None) -> dict:
+    def enqueue_device(self, d_iq: torch.Tensor, marks: list | None = None, peaks_out: torch.Tensor | None = None) -> dict:
         """Enqueue acquisition, hand-off and tracking of IQ resident in HBM on the current stream (three
         launches back to back; the peak table travels to pinned memory on a side stream).  Returns the
         context finish() needs; nothing here waits for the GPU.  `marks` (optional) receives four timing
@@ -138,6 +138,11 @@ class ColdStartPipeline:
         self.acq.launch(d_iq)
         mark()
         got = self._peaks_to_host_async()
+        if peaks_out is not None:
+            # a device copy of this step's peak table for the caller (multi-GPU: what the all-gather sends), in stream
+            # order between acquisition and tracking: on a side stream it would wait for SM room behind the tracking
+            # launches in flight
+            peaks_out.copy_(self.acq.peaks_device(), non_blocking=True)
         self._handoff(n)
         mark()
         self._trk.launch(d_iq)
@@ -168,7 +173,7 @@ class ColdStartPipeline:
         staging memory, valid until three further collect() / process_host() calls."""
         return self._trk.fetch(copy=copy)[:self._n_active]
 
-    def enqueue_host(self, host_iq: torch.Tensor, pieces: int = 4) -> dict:
+    def enqueue_host(self, host_iq: torch.Tensor, pieces: int = 4, peaks_out: torch.Tensor | None = None) -> dict:
         """Enqueue one end-to-end step from pinned host IQ: the upload is cut into `pieces` segments on
         a copy stream; acquisition starts as soon as the dwell has landed and tracking follows the
         upload piece by piece (state carried on the device, records appended), so H2D and compute
@@ -197,6 +202,8 @@ class ColdStartPipeline:
         comp.wait_event(events[0])
         self.acq.launch(d[:2 * first])
         got = self._peaks_to_host_async()
+        if peaks_out is not None:
+            peaks_out.copy_(self.acq.peaks_device(), non_blocking=True)
         self._handoff(n)
         for hi, ev in zip(bounds, events):
             comp.wait_event(ev)
@@ -240,20 +247,20 @@ class ColdStartPool:
         self._next = (i + 1) % len(self.lanes)
         return i
 
-    def submit_device(self, d_iq: torch.Tensor, marks: list | None = None) -> int:
+    def submit_device(self, d_iq: torch.Tensor, marks: list | None = None, peaks_out: torch.Tensor | None = None) -> int:
         i = self._lane()
         s = self._streams[i]
         s.wait_stream(torch.cuda.current_stream())               # the caller's work on d_iq is ordered first
         with torch.cuda.stream(s):
-            ctx = self.lanes[i].enqueue_device(d_iq, marks)
+            ctx = self.lanes[i].enqueue_device(d_iq, marks, peaks_out)
         self._ticket += 1
         self._pending[self._ticket] = (i, ctx)
         return self._ticket
 
-    def submit_host(self, host_iq: torch.Tensor, pieces: int = 4) -> int:
+    def submit_host(self, host_iq: torch.Tensor, pieces: int = 4, peaks_out: torch.Tensor | None = None) -> int:
         i = self._lane()
         with torch.cuda.stream(self._streams[i]):
-            ctx = self.lanes[i].enqueue_host(host_iq, pieces)
+            ctx = self.lanes[i].enqueue_host(host_iq, pieces, peaks_out)
         self._ticket += 1
         self._pending[self._ticket] = (i, ctx)
         return self._ticket
