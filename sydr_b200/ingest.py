@@ -338,7 +338,10 @@ class StreamingReceiver:
                         channel_ids: dict | None = None):
         """Whole file into a `DatabaseHandler` (sydr_b200.io.database, the reference's SQLite format):
         one `channel` row and one `acquisition` row per tracked satellite, one `tracking` row per
-        channel-epoch, inserted column-wise per chunk while the next chunk is on the GPU.
+        channel-epoch, inserted column-wise per chunk while the next chunk is on the GPU, and (want_bits) one
+        `decoding` row per decoded LNAV subframe -- the DECODING_UPDATE packets of the reference's run()
+        (channel_l1ca_borre.py:455-573: the K-NAV bits go through the same preamble search / subframe
+        synchronisation, `lnav_frame.advance_frame`, with `subframe_id`, `tow` and `bits` as the packet carries them).
         `time_sample` is the receiver's sample counter at the millisecond tick on which the reference
         would have emitted the packet (sydr/receiver/receiver.py:120-139, 357-360); `time` is the
         wall clock (`wall_time()` if given, for reproducible files).  `channel_ids` maps PRN -> channel id
@@ -348,14 +351,29 @@ class StreamingReceiver:
         from .io.database import cn0_column
         if not self.want_records:
             raise L.SydrError("run_to_database needs want_records=True")
+        from .channel.lnav_frame import advance_frame
+        from .utils.constants import LNAV_SUBFRAME_SIZE, LNAV_WORD_SIZE
+        from .utils.enumerations import ChannelMessage, TrackingFlags
+
+        class _Frame:                                # what advance_frame works on (the channel classes' members)
+            def __init__(self):
+                self.navBitBufferSize = LNAV_SUBFRAME_SIZE + 2 * LNAV_WORD_SIZE + 2
+                self.navBitsBuffer = np.zeros(self.navBitBufferSize, dtype=int)
+                self.navBitsCounter = 0
+                self.preambuleFound = False
+                self.trackFlags = TrackingFlags.BIT_SYNC
+
         now = wall_time or _time.time
         spm = int(self.fs * 1e-3)
         chans, done = [], None
-        rows = 0
+        frames, bits_done = [], []
+        rows = decoded_rows = 0
         for res in self.run(skip_samples, max_samples):
             if "peaks" in res:
                 chans = res["channels"]
                 done = [0] * len(chans)
+                frames = [_Frame() for _ in chans]
+                bits_done = [0] * len(chans)
                 dwell = self.acq.required_samples
                 cids = [k if channel_ids is None else int(channel_ids[ch["prn"]]) for k, ch in enumerate(chans)]
                 for cid, ch in zip(cids, chans):
@@ -384,7 +402,25 @@ class StreamingReceiver:
                 cn0 = cn0_column(done[k], len(rec), s if 0 <= s < done[k] + len(rec) else -1)
                 database.addTrackingRecords(cid, rec, time=float(now()), time_sample=tick, cn0=cn0,
                                             kaplan=res["kaplan"][k] if "kaplan" in res else None)
+                # navigation bits of this chunk -> preamble search / subframe sync -> DECODING_UPDATE rows.  Bit j of a
+                # channel ends with epoch sync + 20 (j + 1) - 1 (channel_l1ca_borre.py:455-470), an epoch of this chunk.
+                if "bits" in res and s >= 0:
+                    fr = frames[k]
+                    for b in res["bits"][k]:
+                        fr.navBitsBuffer[fr.navBitsCounter] = int(b)
+                        fr.navBitsCounter += 1
+                        j = bits_done[k]
+                        bits_done[k] += 1
+                        got = advance_frame(fr)
+                        if got is None:
+                            continue
+                        tow, subframe_id, subframe_bits = got
+                        e = min(max(s + 20 * (j + 1) - 1 - done[k], 0), len(rec) - 1)
+                        database.addData("decoding", {"cid": cid, "type": ChannelMessage.DECODING_UPDATE, "subframe_id": int(subframe_id),
+                                                      "tow": tow, "bits": subframe_bits, "channel_id": cid, "time": float(now()),
+                                                      "time_sample": int(tick[e])})
+                        decoded_rows += 1
                 done[k] += len(rec)
                 rows += len(rec)
             database.commit()
-        return dict(channels=chans, tracking_rows=rows)
+        return dict(channels=chans, tracking_rows=rows, decoding_rows=decoded_rows)

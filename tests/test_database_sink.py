@@ -87,3 +87,59 @@ def test_batched_commit_is_much_faster_than_one_statement_per_row(tmp_path):
     assert len(db.fetchTable("tracking")) == n
     assert n / dt > 100_000, f"{n / dt:.0f} rows/s"
     db.close()
+
+
+def test_fast_path_writes_the_decoding_rows(golden, tmp_path):
+    """run_to_database (ReceiverGPSL1CA.run_fast / main.py --fast) emits the reference's DECODING_UPDATE rows: the
+    navigation bits of every chunk go through the same preamble search / subframe synchronisation as the channel class
+    (channel_l1ca_borre.py:455-573).  Driven here without a GPU: a stand-in for the streaming loop delivers synthetic
+    parity-clean LNAV bits in uneven chunks; the rows must be the subframes the live reference channel decoded from the
+    same bit stream (tests/golden/framing.npz), stamped with the tick of the epoch that completed the subframe."""
+    import pickle
+    import sqlite3
+    from types import SimpleNamespace
+    import make_golden as MG
+    from sydr_b200 import _lib as L
+    from sydr_b200.ingest import StreamingReceiver
+    from sydr_b200.io.database import DatabaseHandler
+    bits = np.asarray(MG.lnav_stream(seed=5, n_subframes=4, lead=37), dtype=np.int8)
+    found = golden("framing.npz")["found_clean"]                  # [bit index, subframe id, tow, 300 bits]
+    fs, spm, sync, n_ep0 = 4e6, 4000, 137, 137 + 20 * len(bits)
+    start0 = 36001
+
+    def epochs(lo, hi):                                           # epochs lo .. hi-1 of a channel with 4000-sample epochs
+        rec = np.zeros(hi - lo, dtype=L.TRK_EPOCH_DTYPE)
+        rec["start"] = start0 + spm * np.arange(lo, hi)
+        rec["n"] = spm
+        return rec
+
+    rx = object.__new__(StreamingReceiver)
+    rx.fs, rx.want_records, rx.want_bits = fs, True, True
+    rx.acq = SimpleNamespace(required_samples=40000)
+    rx._nav = SimpleNamespace(states=lambda: {"sync_epoch": np.array([sync])})
+    peaks = np.zeros(1, dtype=L.ACQ_PEAK_DTYPE)
+    peaks["prn"], peaks["ratio"] = 5, 3.0
+
+    def fake_run(skip_samples=0, max_samples=None):
+        yield dict(peaks=peaks, channels=[dict(prn=5, carrier_freq=1250.0, start_sample=start0)])
+        cuts = [0, 1000, 1003, 9000, 15001, n_ep0]               # chunk borders in epochs, on and off bit borders
+        for lo, hi in zip(cuts[:-1], cuts[1:]):
+            b_lo, b_hi = max(0, (lo - sync) // 20), max(0, (hi - sync) // 20)      # bits completed inside [lo, hi)
+            yield dict(epochs=[epochs(lo, hi)], bits=[bits[b_lo:b_hi]])
+    rx.run = fake_run
+    db = DatabaseHandler(str(tmp_path / "fast.db"), overwrite=True)
+    out = rx.run_to_database(db, wall_time=lambda: 0.0)
+    db.commit()
+    assert out["tracking_rows"] == n_ep0 and out["decoding_rows"] == len(found) >= 2
+    con = sqlite3.connect(str(tmp_path / "fast.db"))
+    rows = con.execute("select channel_id, time_sample, subframe_id, tow, bits from decoding order by id").fetchall()
+    con.close()
+    assert len(rows) == len(found)
+    for row, ref in zip(rows, found):
+        j = int(ref[0])                                           # the bit that completed the subframe
+        e = sync + 20 * (j + 1) - 1
+        end = start0 + spm * (e + 1)
+        assert row[0] == 0 and row[1] == -(-end // spm) * spm
+        assert [row[2], row[3]] == [int(ref[1]), int(ref[2])]
+        stored = row[4] if isinstance(row[4], str) else pickle.loads(row[4])       # the packet's `bits` as the sink stores its type
+        assert [int(c) for c in stored] == [int(c) for c in ref[3:]]
