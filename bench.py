@@ -673,16 +673,20 @@ def main():
     # ---- warm-up, then K steps resident in HBM
     run_steps(args.warmup, lambda m: pool.submit_device(d_iq, m, peaks_slot()), False)
     sampler = ClockSampler(local)
-    sampler.start()                                     # (NVML start-up takes milliseconds: before the barrier)
+    if rank == 0:
+        sampler.start()                                 # (NVML start-up takes milliseconds: before the barrier); rank 0's GPU only
     lib.sydr_reset_launch_count()
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
     k_ev = []
     barrier()                                           # every rank enters the timed region together
     ev[0].record()
     run_steps(args.steps, lambda m: pool.submit_device(d_iq, m, peaks_slot()), False, k_ev)
+    torch.cuda.synchronize()
+    ev[2].record()                                      # this rank's own steps are done (diagnostics: per_rank_ms)
     barrier()
     ev[1].record()
     torch.cuda.synchronize()
+    ms_own = ev[0].elapsed_time(ev[2])
     launches = int(lib.sydr_launch_count())
     ms_dev = ev[0].elapsed_time(ev[1])
     ms_acq = float(np.mean([m[0].elapsed_time(m[1]) for m in k_ev]))
@@ -725,7 +729,7 @@ def main():
     e1.record()
     torch.cuda.synchronize()
     ms_e2e = e0.elapsed_time(e1)
-    clocks = sampler.stop()
+    clocks = sampler.stop() if rank == 0 else None
 
     # ---- the gathered peak tables of the last steps are read: every rank's 32 records, 12 satellites found on each
     gathered_ok = None
@@ -748,9 +752,14 @@ def main():
             acq_split = {"error": f"{type(exc).__name__}: {exc}"}
 
     t = torch.tensor([ms_dev, ms_e2e], dtype=torch.float64, device=dev)
+    per_rank = torch.tensor([ms_own], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        allr = torch.empty(world, dtype=torch.float64, device=dev)
+        dist.all_gather_into_tensor(allr, per_rank)
+        per_rank = allr
     ms_dev, ms_e2e = float(t[0]), float(t[1])
+    per_rank_ms = [round(float(v), 3) for v in per_rank.cpu()]
     total_samples = float(chunk_samples) * world * args.steps
     value = total_samples / (ms_dev * 1e-3) / 1e6
     e2e = total_samples / (ms_e2e * 1e-3) / 1e6
@@ -829,7 +838,10 @@ def main():
                 "config": workload_config(args, world), "clocks": clocks,
                 "e2e": {"value": e2e, "unit": "Msamples/s", "rtf": e2e * 1e6 / FS / world,
                         "h2d_bytes_per_step": int(host.numel() * host.element_size()), "d2h_bytes_per_step": int(d2h_bytes)},
-                "gpu_launches": launches, "roofline": roofline}
+                "gpu_launches": launches, "per_rank_ms": per_rank_ms,
+                "per_rank_note": "each rank's own K steps (device time up to its last result), before the closing barrier; the line's "
+                                 "ms_per_step is the region between the two barriers, max over ranks",
+                "roofline": roofline}
         if acq_split is not None:
             line["acq_split"] = acq_split
             line["gathered_peak_tables_ok"] = gathered_ok

@@ -223,6 +223,14 @@ int sydr_trk_run(const void* d_iq, int iq_dtype, long long iq_alloc_samples, dou
  * reduction + send, gather wait, loop closure, gather totals; [15] = epochs).  NULL = off. */
 int sydr_trk_profile_buffer(long long* d_buf);
 
+/* Diagnostics / tuning of the prefix-moment kernel (cfg.kernel = 1): debug flags (bit 1: skip the exact re-evaluation
+ * of ambiguous samples), and the launch shape -- correlating warps per channel (2, 4, 6, 8) and producer warps per CTA
+ * (1 .. 4) -- of the following launches.  With a profile buffer set, the kernel's diagnostics instantiation fills
+ * [0..7] = total, gather issue, entry wait, barrier, correlate cycles, waits, rounds, epochs of warp 2 and
+ * [8..12] = producer total, ring wait, blocks, load + scan, store cycles. */
+int sydr_trkm_debug(int flags);
+int sydr_trkm_shape(int correlating_warps, int producer_warps);
+
 /* Diagnostics / tests: which correlator formulation K-TRK uses.  0 (default) = automatic: the
  * half-chip segment path wherever the spacings are multiples of half a chip and the sampling
  * rate fits, else the chunk paths; 1 = chunk paths only.  Results agree to rounding. */

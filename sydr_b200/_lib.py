@@ -125,6 +125,8 @@ SIGNATURES = {
     "sydr_trk_run_kaplan": (_i, [_vp, _i, _ll, _d, _vp, _vp, _i, _vp, _vp, _i, _vp, _vp, _vp]),
     "sydr_trk_profile_buffer": (_i, [_vp]),
     "sydr_trk_set_mode": (_i, [_i]),
+    "sydr_trkm_debug": (_i, [_i]),
+    "sydr_trkm_shape": (_i, [_i, _i]),
     "sydr_trk_state_init": (_i, [_vp, _i, _d, _d, _ll] + [_d] * 11),
     "sydr_convert_to_f32": (_i, [_vp, _i, _ll, _vp, _vp]),
     "sydr_acq_handoff": (_i, [_vp, _i, _d, _d, _d, _ll, _ll, _ll, _d, _vp, _ll, _vp, _i, _vp, _vp]),
