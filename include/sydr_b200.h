@@ -200,7 +200,8 @@ typedef struct {
     int32_t kernel;         /* 0 = automatic; 1 = prefix-moment kernel (throughput shape: the samples of a recording are
                                turned into prefix moments once, every channel gathers from them; int16 IQ, Borre loops);
                                2 = per-channel kernels only                                          */
-    int32_t group;          /* prefix-moment kernel: correlating warps per channel (2, 4, 6, 8); 0 = default (4) */
+    int32_t group;          /* prefix-moment kernel: consecutive channels per CTA (1 .. 4, same recording); 0 = the
+                               smallest group whose CTAs fit one wave of the SMs                     */
     int32_t rec_channels;   /* prefix-moment kernel: channel slots per recording -- channels
                                [r*rec_channels, (r+1)*rec_channels) share recording r; 0 = all the channels are on
                                one recording (a channel that is not on its slot's recording is served by the
@@ -223,11 +224,8 @@ int sydr_trk_run(const void* d_iq, int iq_dtype, long long iq_alloc_samples, dou
  * reduction + send, gather wait, loop closure, gather totals; [15] = epochs).  NULL = off. */
 int sydr_trk_profile_buffer(long long* d_buf);
 
-/* Diagnostics / tuning of the prefix-moment kernel (cfg.kernel = 1): debug flags (bit 1: skip the exact re-evaluation
- * of ambiguous samples), and the launch shape -- correlating warps per channel (2, 4, 6, 8) and producer warps per CTA
- * (1 .. 4) -- of the following launches.  With a profile buffer set, the kernel's diagnostics instantiation fills
- * [0..7] = total, gather issue, entry wait, barrier, correlate cycles, waits, rounds, epochs of warp 2 and
- * [8..12] = producer total, ring wait, blocks, load + scan, store cycles. */
+/* Diagnostics of the prefix-moment kernel (cfg.kernel = 1): debug flags (bit 1: skip the exact re-evaluation of ambiguous
+ * samples); sydr_trkm_shape is kept for the ABI and does nothing (the launch shape is fixed). */
 int sydr_trkm_debug(int flags);
 int sydr_trkm_shape(int correlating_warps, int producer_warps);
 

@@ -702,9 +702,7 @@ static int trk_run_impl(const void* d_iq, int iq_dtype, long long iq_alloc_sampl
     if (moments) {
         TrkParams PL = P;
         PL.use_tma = 1;
-        const int cw = cfg ? cfg->group : 0;
-        set_scale(PL, cw > 0 ? cw : 2);
-        const int rc2 = launch_trkm(PL, n_channels, cfg ? cfg->rec_channels : 0, cw, s);
+        const int rc2 = launch_trkm(PL, n_channels, cfg ? cfg->rec_channels : 0, cfg ? cfg->group : 0, s);
         if (rc2 == SYDR_ERR_UNSUPPORTED && kernel_sel == 0) moments = false;       // more channels on one recording than the device holds: per-channel kernels
         else if (rc2 != SYDR_OK) return rc2;
     }

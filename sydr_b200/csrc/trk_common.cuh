@@ -1103,6 +1103,6 @@ __device__ __forceinline__ void carrier_close_kaplan(SH& sh, CarrierState& st, K
 
 
 // trkm.cu: the prefix-moment formulation (throughput shape).  `group` consecutive channels share a CTA and a recording.
-int launch_trkm(const TrkParams& P, int n_channels, int rec_channels, int cw, cudaStream_t s);
+int launch_trkm(const TrkParams& P, int n_channels, int rec_channels, int group, cudaStream_t s);
 
 }  // namespace sydr

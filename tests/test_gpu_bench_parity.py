@@ -132,13 +132,13 @@ def test_headline_chunk_dense_pool_vs_oracle():
 
 
 SHAPES = {"cta_per_channel": dict(cluster=1, threads=256, use_tma=False, kernel=2),      # LEAN instantiation of trk.cu
-          "moments_w4": dict(kernel=1, group=4), "moments_w8": dict(kernel=1, group=8), "moments_w2": dict(kernel=1, group=2)}
+          "moments_g3": dict(kernel=1, group=3), "moments_g4": dict(kernel=1, group=4), "moments_g1": dict(kernel=1, group=1)}
 
 
 @pytest.mark.parametrize("shape", list(SHAPES))
 def test_throughput_instantiation_vs_oracle(shape):
     """configs[4] shape: 3 recordings x 12 channels x 0.5 s in one launch of the throughput kernels: the
-    prefix-moment kernel (trkm.cu, what bench.throughput_stress launches; 4 / 8 / 2 correlating warps per channel) and the
+    prefix-moment kernel (trkm.cu, what bench.throughput_stress launches; 3 / 4 / 1 channels per CTA) and the
     per-channel LEAN instantiation of trk.cu."""
     import torch
     from sydr_b200 import synth

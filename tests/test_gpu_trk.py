@@ -136,7 +136,7 @@ CONFIGS = [dict(cluster=1, threads=0, use_tma=True), dict(cluster=2, threads=0, 
            # the DENSE instantiation bench.py's timed region launches (ColdStartPool, several steps in flight)
            dict(cluster=0, threads=0, use_tma=True, dense=True), dict(cluster=8, threads=160, use_tma=True, dense=True),
            # the prefix-moment kernel (trkm.cu; int16 IQ only: at fs4 / int8 it must hand every channel to the general kernel)
-           dict(cluster=0, threads=0, use_tma=True, kernel=1, group=4), dict(cluster=0, threads=0, use_tma=True, kernel=1, group=2)]
+           dict(cluster=0, threads=0, use_tma=True, kernel=1, group=1), dict(cluster=0, threads=0, use_tma=True, kernel=1, group=2)]
 
 
 @pytest.mark.parametrize("name", ["fs4", "fs25"])

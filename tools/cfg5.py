@@ -46,9 +46,9 @@ def main():
     if os.environ.get("TRKM_PROF"):           # cycle counters of the prefix-moment kernel (diagnostics instantiation)
         prof = torch.zeros(n_ch * 16, dtype=torch.int64, device="cuda")
         L.load().sydr_trk_profile_buffer(prof.data_ptr())
-    # (cluster, threads, tma[, kernel, group]): kernel 1 = prefix-moment kernel (trkm.cu; group = correlating warps per channel),
+    # (cluster, threads, tma[, kernel, group]): kernel 1 = prefix-moment kernel (trkm.cu; group = channels per CTA),
     # 2 = per-channel kernels (trk.cu)
-    shapes = [(0, 0, 1, 1, 4), (0, 0, 1, 1, 8), (0, 0, 1, 1, 2), (1, 256, 0, 2, 0)]
+    shapes = [(0, 0, 1, 1, 3), (0, 0, 1, 1, 4), (0, 0, 1, 1, 2), (1, 256, 0, 2, 0)]
     if len(sys.argv) > 3:
         shapes = [tuple(int(v) for v in a.split(",")) for a in sys.argv[3:]]
     for shp in shapes:

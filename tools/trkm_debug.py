@@ -9,7 +9,7 @@ from sydr_b200.engine import AcquisitionEngine, TrackingEngine, make_trk_states
 
 FS = 25e6
 n_rec, seconds = int(sys.argv[1]) if len(sys.argv) > 1 else 3, float(sys.argv[2]) if len(sys.argv) > 2 else 0.5
-group = int(sys.argv[3]) if len(sys.argv) > 3 else 4
+group = int(sys.argv[3]) if len(sys.argv) > 3 else 3
 n = int(round(seconds * FS)); pad = 2048
 buf = torch.zeros(n_rec * (2 * n + pad) + 4096, dtype=torch.int16, device="cuda")
 acq = AcquisitionEngine(FS, 0.0, 5000.0, 250.0, 1, 10, list(synth.PRNS_12))
