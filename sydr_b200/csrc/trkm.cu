@@ -79,6 +79,7 @@ struct MChan {                // shared-memory state of one channel
 struct MShared {
     MChan chan[kMMaxGroup];
     float fix[kMWarps][8];                      // exact-evaluation corrections of ambiguous samples, per warp
+    int ep[kMWarps][kMMaxGroup];                // per warp and channel: the epoch the warp's next block starts in (never decreases)
     long long origin;                           // recording-relative sample of block 0's first sample (multiple of 4)
     long long valid_lo, valid_hi;               // samples readable from the recording's base pointer
     long long iq_base, limit;
@@ -291,6 +292,7 @@ __device__ __forceinline__ void m_close(const TrkmParams& PM, MShared& sh, MChan
     m_publish(PM, sh, ch, e + 1, lane);
 }
 
+template <bool PROF>
 __global__ void __launch_bounds__(kMThreads, 1) trkm_kernel(const TrkmParams PM) {
     extern __shared__ __align__(1024) uint8_t dyn_smem[];
     __shared__ __align__(16) MShared sh;
@@ -406,25 +408,57 @@ __global__ void __launch_bounds__(kMThreads, 1) trkm_kernel(const TrkmParams PM)
     __syncthreads();
 
     // ---- the blocks
-    int ep[kMMaxGroup];                             // per channel: the epoch this warp's next block starts in (never decreases)
-#pragma unroll
-    for (int c = 0; c < kMMaxGroup; ++c) ep[c] = 0;
+    int* ep = sh.ep[warp];
+    if (lane < kMMaxGroup) ep[lane] = 0;
+    __syncwarp();
     float* fix = sh.fix[warp];
+    long long pt0 = 0, pt = 0, c_prod = 0, c_piece = 0, c_wait = 0, c_close = 0, n_blk = 0, n_piece = 0, n_close = 0;
+    if (PROF) pt0 = clock64();
     while (sh.ok) {
+        if (PROF) pt = clock64();
         int t = 0;
         if (lane == 0) t = (sh.running > 0) ? atomicAdd(&sh.next_block, 1) : 0x7fffffff;
         t = __shfl_sync(full, t, 0);                                  // (one lane looks: the whole warp leaves or stays)
         if (t >= sh.n_blocks) break;
         m_produce(PM, sh, slot, t, lane);
+        if (PROF) { const long long now = clock64(); c_prod += now - pt; pt = now; ++n_blk; }
         const int s_lo = t * kMNew, s_hi = s_lo + kMNew;              // the samples whose segments this block owns (block-0 relative)
         unsigned todo = 0;
         for (int c = 0; c < G; ++c)
             if (sh.chan[c].active) todo |= 1u << c;
+        // The channel whose epoch ends soonest behind this block's first sample goes first: its pieces are what the next loop
+        // closure waits for, and the warps with later blocks wait for that closure.
+        int order = 0;
+        {
+            int key[kMMaxGroup];
+#pragma unroll
+            for (int c = 0; c < kMMaxGroup; ++c) {
+                key[c] = 0x7fffffff;
+                if (c < G && (todo >> c & 1u)) {
+                    const MChan& ch = sh.chan[c];
+                    const int e = ep[c];
+                    if (ch.pub >= e && ch.stop_epoch > e) {
+                        const MCtl& ctl = ch.ctl[e & 1];
+                        long long k = ctl.a - sh.origin + ctl.n - s_lo;    // samples from the block's start to the epoch's end
+                        if (k <= 0) k += ctl.n;                            // (that epoch is over: its successor's end, roughly)
+                        key[c] = (int)min(k, 0x7ffffff0LL);
+                    }
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < kMMaxGroup; ++c) {
+                int rank = 0;
+#pragma unroll
+                for (int d = 0; d < kMMaxGroup; ++d) rank += (key[d] < key[c] || (key[d] == key[c] && d < c)) ? 1 : 0;
+                order |= c << (2 * rank);
+            }
+            order = __shfl_sync(full, order, 0);                          // one lane's view for all
+        }
         int spins = 0;
         while (todo) {
             bool progressed = false;
-#pragma unroll
-            for (int c = 0; c < kMMaxGroup; ++c) {
+            for (int k = 0; k < kMMaxGroup; ++k) {
+                const int c = (order >> (2 * k)) & 3;
                 if (c >= G || !(todo >> c & 1u)) continue;
                 MChan& ch = sh.chan[c];
                 // one (block, epoch) piece per pass: the part of epoch ep[c] that starts inside this block
@@ -514,16 +548,30 @@ __global__ void __launch_bounds__(kMThreads, 1) trkm_kernel(const TrkmParams PM)
                 if (lane == 0) last = (atomicAdd(&ch.cnt[e & 1], 1) + 1 == ctl.n_blocks) ? 1 : 0;
                 last = __shfl_sync(full, last, 0);
                 const bool ends_here = a_rel + n <= s_hi;              // the epoch ends inside this block
+                if (PROF) { const long long now = clock64(); c_piece += now - pt; pt = now; ++n_piece; }
                 if (last) {
                     __threadfence_block();
                     m_close(PM, sh, ch, e, lane);
+                    if (PROF) { const long long now = clock64(); c_close += now - pt; pt = now; ++n_close; }
                 }
                 if (ends_here) ep[c] = e + 1;
                 if (a_rel + n >= s_hi) todo &= ~(1u << c);             // (else the successor's first piece is in this block too)
                 progressed = true;
             }
-            if (!progressed) __nanosleep(spins++ < 4 ? 100 : 400);     // every open channel waits for a loop closure
-            else spins = 0;
+            if (!progressed) {
+                __nanosleep(spins++ < 4 ? 100 : 400);                  // every open channel waits for a loop closure
+                if (PROF) { const long long now = clock64(); c_wait += now - pt; pt = now; }
+            } else {
+                spins = 0;
+            }
+        }
+    }
+    if (PROF && P.prof != nullptr && lane == 0 && warp < 4 && ch_lo + (warp % max(G, 1)) < PM.n_channels) {
+        // diagnostics: warps 0 .. G-1 of the CTA leave their cycle counters in the rows of the CTA's channels
+        if (warp < G) {
+            long long* pc = P.prof + (long long)(ch_lo + warp) * 16;
+            pc[0] = clock64() - pt0; pc[1] = c_prod; pc[2] = c_piece; pc[3] = c_wait; pc[4] = c_close;
+            pc[5] = n_blk; pc[6] = n_piece; pc[7] = n_close;
         }
     }
     __syncthreads();
@@ -589,8 +637,9 @@ int launch_trkm(const TrkParams& P0, int n_channels, int rec_channels, int group
     PM.alpha_hc_max = 0.06;
     PM.debug = g_trkm_debug;
     const size_t smem = (size_t)kMWarps * kMSlotBytes;
-    SYDR_CUDA_CHECK(cudaFuncSetAttribute(trkm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    trkm_kernel<<<n_rec * PM.groups_per_rec, kMThreads, smem, s>>>(PM);
+    auto kern = (P0.prof != nullptr) ? trkm_kernel<true> : trkm_kernel<false>;
+    SYDR_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<n_rec * PM.groups_per_rec, kMThreads, smem, s>>>(PM);
     count_launch();
     SYDR_CUDA_CHECK(cudaGetLastError());
     return SYDR_OK;

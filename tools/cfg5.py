@@ -68,13 +68,12 @@ def main():
         res = eng.fetch()
         if prof is not None and kernel == 1:
             pc = prof.cpu().numpy().reshape(-1, 16).astype(float)
-            ep = np.maximum(pc[:, 7], 1)
-            print("   consumer warp 2, cycles per epoch (mean / min / max over channels): " + "  ".join(
+            pc = pc[pc[:, 0] > 0]
+            ep = nep_mean = float(np.mean([len(r) for r in res]))
+            print("   one warp per CTA, cycles per epoch (mean / min / max over CTAs): " + "  ".join(
                 f"{nm} {(pc[:, i] / ep).mean():.0f}/{(pc[:, i] / ep).min():.0f}/{(pc[:, i] / ep).max():.0f}"
-                for i, nm in ((0, "total"), (1, "top+gather issue"), (2, "e0 valid"), (13, "math"), (14, "amb"), (15, "n_amb"), (3, "barrier A"), (4, "correlate"), (5, "sleeps"), (6, "rounds"))))
-            nb = np.maximum(pc[:, 10], 1)
-            print("   producer warp, cycles per block: " + "  ".join(f"{nm} {(pc[:, i] / nb).mean():.0f}/{(pc[:, i] / nb).min():.0f}/{(pc[:, i] / nb).max():.0f}"
-                  for i, nm in ((9, "ring wait"), (11, "load+scan"), (12, "store+fence"))) + f"  blocks per warp {pc[:, 10].mean():.0f}  total cycles {pc[:, 8].mean():.3g}")
+                for i, nm in ((0, "total"), (1, "moments"), (2, "pieces"), (3, "waiting"), (4, "closures"))) +
+                f"   per epoch: blocks {pc[:, 5].mean() / ep:.2f} pieces {pc[:, 6].mean() / ep:.2f} closures {pc[:, 7].mean() / ep:.2f}")
         nep = np.array([len(r) for r in res])
         err = np.array([abs(r["carrier_freq"][-1] - t) for r, t in zip(res, truth)])
         ms = min(ts)
