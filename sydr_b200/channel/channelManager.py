@@ -73,8 +73,15 @@ class ChannelManager:
             if channel.channelState is ChannelState.IDLE:
                 channel.setSatellite(satelliteID)
                 channel.start()
-                self._abs_cur[channel.channelID] = self._written + channel.currentSample - self.sharedBuffer.idxWrite \
+                start = self._written + channel.currentSample - self.sharedBuffer.idxWrite \
                     if self.sharedBuffer.full else channel.currentSample
+                if start < self._base:
+                    # the device buffer has been compacted past the ring position the channel wants to start from (the
+                    # reference's ring keeps 100 ms; _compact keeps that much behind the write position, so this means a
+                    # start further back than the ring itself holds)
+                    raise L.SydrError(f"channel {channel.channelID}: start sample {start} lies before the oldest sample "
+                                      f"kept on the device ({self._base})")
+                self._abs_cur[channel.channelID] = start
                 logging.getLogger(__name__).debug(f"CID {channel.channelID} initialised to satellite [G{satelliteID}].")
                 return channel
         raise Warning(f"Could not find an IDLE channel for tracking satellite [G{satelliteID}].")
@@ -96,6 +103,11 @@ class ChannelManager:
         """Allocate the device buffer for the first block's representation."""
         if self._d_iq is not None:
             return
+        if sample.dtype in (np.int8, np.int16) and not getattr(self.rfSignal, "isComplex", True):
+            # real-valued integer samples are not interleaved I,Q pairs (rfsignal.py:107-126): reading them as pairs would
+            # silently halve the sample count
+            raise L.SydrError("ChannelManager: real-valued integer samples are not supported (is_complex = false); "
+                              "pass complex samples")
         if sample.dtype == np.int8:
             self._iq_dtype, tdt, per = L.IQ_I8, torch.int8, 2
         elif sample.dtype == np.int16:
@@ -120,8 +132,10 @@ class ChannelManager:
     def _compact(self):
         """Drop the samples every channel has consumed: move the tail of the device buffer to its
         start and rebase the device-side channel states."""
-        keep_from = min([self._written] + [c for cid, c in self._abs_cur.items()
-                                            if self.channels[cid].channelState is not ChannelState.IDLE])
+        # what a channel started later may still ask for: one ring length behind the write position (requestTracking)
+        ring = int(getattr(self.sharedBuffer, "maxSize", 0))
+        keep_from = min([max(self._written - ring, self._base)] + [c for cid, c in self._abs_cur.items()
+                                                                    if self.channels[cid].channelState is not ChannelState.IDLE])
         keep_from -= keep_from % 16
         shift = keep_from - self._base
         if shift <= 0:

@@ -366,7 +366,7 @@ class StreamingReceiver:
         now = wall_time or _time.time
         spm = int(self.fs * 1e-3)
         chans, done = [], None
-        frames, bits_done = [], []
+        frames, bits_done, last_tick = [], [], []
         rows = decoded_rows = 0
         for res in self.run(skip_samples, max_samples):
             if "peaks" in res:
@@ -374,6 +374,7 @@ class StreamingReceiver:
                 done = [0] * len(chans)
                 frames = [_Frame() for _ in chans]
                 bits_done = [0] * len(chans)
+                last_tick = [-(1 << 62)] * len(chans)
                 dwell = self.acq.required_samples
                 cids = [k if channel_ids is None else int(channel_ids[ch["prn"]]) for k, ch in enumerate(chans)]
                 for cid, ch in zip(cids, chans):
@@ -396,7 +397,13 @@ class StreamingReceiver:
                 if not len(rec):
                     continue
                 end = (rec["start"] + rec["n"]).astype(np.int64)
+                # the receiver ticks once per millisecond and a channel emits at most one epoch per tick
+                # (channel.py:121-160): tick_k = max(ceil(end_k / spm) spm, tick_{k-1} + spm), a running maximum
                 tick = -(-end // spm) * spm
+                k_idx = spm * (done[k] + np.arange(len(rec), dtype=np.int64))
+                run = np.maximum.accumulate(np.concatenate(([last_tick[k]], tick - k_idx)))[1:]
+                last_tick[k] = int(run[-1])
+                tick = run + k_idx
                 s = int(sync[k])
                 # a synchronisation found later than this chunk does not reach back into it
                 cn0 = cn0_column(done[k], len(rec), s if 0 <= s < done[k] + len(rec) else -1)
