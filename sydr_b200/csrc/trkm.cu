@@ -59,6 +59,8 @@ struct MCtl {                 // per-epoch constants of one channel, published b
     int n, p0;
     int n_blocks;             // blocks the epoch overlaps: that many deliveries complete it
     int first_block;          // the first of them
+    volatile int epoch;       // which epoch these constants belong to (-1 while they are being rewritten)
+    int pad;
 };
 
 struct MChan {                // shared-memory state of one channel
@@ -227,6 +229,9 @@ __device__ __forceinline__ void m_publish(const TrkmParams& PM, MShared& sh, MCh
         if (!ok || !car_ok) { stop = true; status = kNeedGeneral; }
         if (!stop) {
             MCtl& c = ch.ctl[epoch & 1];
+            if (lane == 0) c.epoch = -1;                                         // (a reader two epochs late must not take a half-written set)
+            __syncwarp();
+            __threadfence_block();
             if (lane < 3) {
                 c.start[lane] = t_start;
                 c.step[lane] = t_step;
@@ -248,13 +253,15 @@ __device__ __forceinline__ void m_publish(const TrkmParams& PM, MShared& sh, MCh
         }
     }
     __syncwarp();
+    __threadfence_block();
     if (lane == 0) {
         ch.status = status;
-        __threadfence_block();
         if (stop) {
             ch.stop_epoch = epoch;
             atomicSub((int*)&sh.running, 1);
         } else {
+            ch.ctl[epoch & 1].epoch = epoch;
+            __threadfence_block();
             ch.pub = epoch;
         }
     }
@@ -468,6 +475,15 @@ __global__ void __launch_bounds__(kMThreads, 1) trkm_kernel(const TrkmParams PM)
                 if (pub < e) continue;                                // not published yet: the other channels first
                 __threadfence_block();
                 const MCtl& ctl = ch.ctl[e & 1];
+                {
+                    // The slot holds epoch e unless this warp comes two or more epochs late (every epoch in between is then
+                    // closed without this block, i.e. lies in front of it): take up the epoch the slot holds now.
+                    const int held = __shfl_sync(full, ctl.epoch, 0);
+                    if (held != e) {
+                        if (held > e) { ep[c] = held; progressed = true; }
+                        continue;
+                    }
+                }
                 const int n = ctl.n;
                 const long long a64 = ctl.a - sh.origin;              // epoch start, block-0 relative
                 if (a64 >= s_hi) { todo &= ~(1u << c); progressed = true; continue; }      // the channel starts behind this block
