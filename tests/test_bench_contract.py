@@ -1,0 +1,45 @@
+"""bench.py's contract pieces that run without a GPU: the reference arm's JSON line (tier contract: same metric / unit /
+config keys as the GPU arm, `impl`, `cpu_baseline` with kind / cores / sample, an `e2e` object with zero copy bytes), the
+tracked DRAM-traffic file the GPU arm reads, and the legacy prototype table against the header."""
+import json
+import os
+import re
+import subprocess
+import sys
+
+import helpers as H  # noqa: F401
+
+
+def test_reference_arm_line():
+    out = subprocess.run([sys.executable, os.path.join(H.ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                          "--chunk-seconds", "0.12", "--ref-budget-s", "4"], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["unit"] == "Msamples/s" and line["higher_is_better"] is True
+    assert line["metric"] == "cold acquisition (32 PRN) + 12-channel tracking throughput"
+    assert line["steps"] == 1 and line["warmup"] == 0 and line["n_gpus"] == 1 and line["value"] > 0
+    assert line["e2e"] == {"value": line["value"], "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    cb = line["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == line["value"] and "PRNs acquired" in cb["sample"]
+    assert cb["trk"]["channels"] == 12 and cb["acq"]["prns"] == 32
+    # a short chunk fits the budget whole: nothing is extrapolated, and the clock is the one that ran
+    assert line["sampled"] is False and abs(line["ms_per_step"] * 1e-3 - line["timed_s"]) < 0.05 * line["timed_s"] + 0.05
+    assert "workload" in line["config"] and "model" not in line["config"]
+
+
+def test_tracked_traffic_file():
+    sys.path.insert(0, H.ROOT)
+    import bench
+    total, info = bench.ncu_traffic(60.0)
+    assert info["file"] == "profiles/ncu_traffic.json" and info["measured_in_this_run"] is False
+    assert os.path.exists(os.path.join(H.ROOT, info["sources"][0]))
+    # the tracking launch reads its samples once: 4 B x 25 MS/s x 60 s, plus the records
+    assert 0.98 * 6.0e9 < info["trk_borre_kernel"] < 1.1 * 6.0e9 and total > info["trk_borre_kernel"]
+
+
+def test_legacy_prototypes_cover_the_header():
+    from sydr_b200.old._legacy import PROTOTYPES
+    hdr = open(os.path.join(H.ROOT, "include", "sydr_b200.h")).read()
+    legacy = re.findall(r"^void\s+([A-Za-z]+)\(", hdr, re.M)
+    legacy = [n for n in legacy if not n.startswith("sydr_")]
+    assert sorted(legacy) == sorted(PROTOTYPES) and len(PROTOTYPES) == 9
