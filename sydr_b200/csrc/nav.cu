@@ -15,7 +15,11 @@
 // One warp owns one channel.  Before synchronisation the lanes test 32 epochs per round and a
 // ballot picks the first sign change; after it every lane owns one bit and adds its 20 prompts
 // in the reference's order (sequential FP64 adds starting from 0.0), so the sums - not only
-// their signs - equal the reference's navPromptSum bit for bit.
+// their signs - equal the reference's navPromptSum bit for bit (nav.npz: every tick of the live reference channel).
+// One prompt per EPOCH goes into a bit.  The reference calls runDecoding on every millisecond TICK; on a tick without a
+// completed epoch (the channel's backlog is below one epoch) it adds the previous epoch's prompt again.  Such ticks do
+// not occur while the epoch length stays within a sample of 1 ms (all the recordings tested); a recording whose code
+// Doppler makes them occur would see that one prompt counted twice by the reference and once here.
 //
 // Quirk kept on purpose: on the synchronisation epoch resetPrompt() zeroes nbPrompt *before*
 // runDecoding reads correlatorsBuffer[nbPrompt - 1], so the first addend of the first bit is
