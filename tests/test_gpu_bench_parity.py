@@ -166,3 +166,68 @@ def test_throughput_instantiation_vs_oracle(shape):
     assert min(len(r) for r in recs) >= 485
     res = check_against_oracle(xs, chans, recs)
     print(f"throughput launch ({shape}) vs oracle:", {k: max(r[k] for r in res) for k in ("e_corr", "e_state", "d_car", "d_code", "d_phase")})
+
+
+def test_full_size_recording_properties():
+    """BASELINE.json configs[2] at FULL size, exactly as bench.py's step runs it: 60 s of 25 MS/s int16 IQ (6 GB) resident in
+    HBM, ColdStartPool -> 32-PRN acquisition, device hand-off, one DENSE tracking launch of 60 000 epochs x 12 channels.  Size-independent properties (the oracle needs ~15 core-minutes for this much): every
+    satellite acquired, every channel tracked to the last millisecond with contiguous epochs, Doppler equal to the
+    generator's truth, and every navigation bit after the pull-in second equal to the transmitted data (up to the Costas
+    half-cycle ambiguity of the whole stream)."""
+    import torch
+    from sydr_b200 import synth
+    from sydr_b200.pipeline import ColdStartPool
+    seconds = 60.0
+    sc = synth.make_scenario(FS, 16, seconds, synth.PRNS_12, 1003, 250.0)
+    d = synth.generate_iq_torch(sc, device="cuda")
+    pool = ColdStartPool(lanes=2, fs=FS, nbits=16, search_prns=list(range(1, 33)), n_channels=12, max_seconds=seconds,
+                         doppler_range=5000.0, doppler_step=250.0, coh=1, noncoh=10)
+    out = pool.result(pool.submit_device(d), records=True, copy=True)
+    pool.close()
+    del d
+    torch.cuda.empty_cache()
+    assert [c["prn"] for c in out["channels"]] == list(synth.PRNS_12)
+    truth = synth.nav_bits_of(sc)
+    for k, (ch, e) in enumerate(zip(out["channels"], out["epochs"])):
+        sat = next(s for s in sc.sats if s.prn == ch["prn"])
+        assert len(e) >= 59985, (ch["prn"], len(e))
+        assert np.array_equal(e["start"][1:], (e["start"] + e["n"])[:-1])                     # contiguous epochs
+        assert (e["start"][-1] + e["n"][-1]) / FS > seconds - 0.002                           # to the last millisecond
+        assert abs(float(np.mean(e["carrier_freq"][-500:])) - sat.doppler) < 5.0
+        assert np.abs(e["n"] - 25000).max() <= 1
+        # navigation bits from the prompt sums (the reference's rule: synchronise on the first sign change after 100 epochs,
+        # then 20 prompts per bit, channel_l1ca_borre.py:398-413, 455-470)
+        ip = e["corr"][:, 2]
+        flips = np.nonzero(np.diff(np.sign(ip)) != 0)[0]
+        sync = int(flips[flips >= 100][0] + 1)
+        n_bits = (len(ip) - sync) // 20
+        b = (ip[sync:sync + 20 * n_bits].reshape(n_bits, 20).sum(axis=1) > 0).astype(np.int8)
+        t_mid = (e["start"][sync] + 10 * FS * 1e-3 + 20 * FS * 1e-3 * np.arange(n_bits)) / FS
+        tx = (truth[ch["prn"]][synth.nav_bit_index(sat, t_mid)] > 0).astype(np.int8)
+        late = t_mid > 1.0
+        agree = float((tx[late] == b[late]).mean())
+        assert agree in (0.0, 1.0) and n_bits >= 2980, (ch["prn"], agree, n_bits)
+
+
+def test_long_horizon_vs_oracle():
+    """10 s x 2 channels (20 000 epochs) of the latency instantiation against BorreTrackOracle, teacher-forced on every epoch
+    and free-running over the whole horizon: the closed loop neither drifts nor mis-assigns a sample over 10 000 epochs."""
+    import torch
+    from sydr_b200 import synth
+    from sydr_b200.engine import AcquisitionEngine, TrackingEngine, make_trk_states
+    seconds, prns = 10.0, (7, 22)
+    sc = synth.make_scenario(FS, 16, seconds, prns, 1711, 250.0)
+    d = synth.generate_iq_torch(sc, device="cuda")
+    acq = AcquisitionEngine(FS, 0.0, 5000.0, 250.0, 1, 10, list(prns))
+    chans = []
+    for p in acq.run(d[:2 * 250000])["peaks"]:
+        carrier, _, cur = acq.handoff(p)
+        chans.append(dict(prn=int(p["prn"]), carrier_freq=carrier, start_sample=cur, iq_len=d.numel() // 2))
+    acq.close()
+    eng = TrackingEngine(FS, make_trk_states(FS, chans), int(seconds * 1000) + 8)
+    recs = eng.run(d)
+    assert min(len(r) for r in recs) >= 9985
+    x = to_c64(d.cpu().numpy())
+    del d
+    res = check_against_oracle(x, chans, recs)
+    print("10 s horizon vs oracle:", {k: max(r[k] for r in res) for k in ("e_corr", "e_state", "d_car", "d_code", "d_phase")})
