@@ -127,3 +127,15 @@ def test_linearity_property_full_size():
     eng.close()
     assert np.array_equal(a["freq_idx"], b["freq_idx"]) and np.array_equal(a["code_idx"], b["code_idx"])
     assert np.allclose(b["peak1"], 2 * a["peak1"], rtol=1e-6) and np.allclose(a["ratio"], b["ratio"], rtol=1e-6)
+
+
+def test_cfg4_sweep_of_the_bench(golden):
+    """bench.py --workload cfg4 on one GPU: the configs[3] sweep through ShardedAcquisition (world 1) equals the table a plain
+    AcquisitionEngine computes, and finds the eight satellites of the recording."""
+    import sys
+    import torch
+    sys.path.insert(0, H.ROOT)
+    import bench
+    r = bench.acq_split_bench(torch.device("cuda", 0), 0, 1, steps=2, warmup=1)
+    assert r["table_identical_to_one_gpu"] and r["table_identical_on_all_ranks"]
+    assert r["prns_found"] == [3, 7, 11, 14, 19, 22, 27, 31] and r["n_gpus"] == 1 and r["ms_per_sweep"] > 0
