@@ -43,3 +43,10 @@ def test_legacy_prototypes_cover_the_header():
     legacy = re.findall(r"^void\s+([A-Za-z]+)\(", hdr, re.M)
     legacy = [n for n in legacy if not n.startswith("sydr_")]
     assert sorted(legacy) == sorted(PROTOTYPES) and len(PROTOTYPES) == 9
+
+
+def test_reference_checker_is_built_when_the_reference_is_mounted():
+    """oracle/_ref/tracking.so (the reference's own tracking.c, compiled by oracle/Makefile) is what tests/test_gpu_legacy.py checks
+    the legacy entry points against; it is built in the container that has /root/reference and travels with the repository."""
+    if os.path.isdir("/root/reference/sydr/c_functions"):
+        assert os.path.exists(os.path.join(H.ROOT, "oracle", "_ref", "tracking.so")), "oracle/Makefile did not produce oracle/_ref/tracking.so"
