@@ -1,18 +1,19 @@
 #!/usr/bin/env python
-"""Headline benchmark: 32-PRN cold acquisition + 12-channel closed-loop tracking on a
-25 MS/s int16 recording (BASELINE.json metric), one process per GPU.
+"""Headline benchmark: 32-PRN cold acquisition + 12-channel closed-loop tracking on 25 MS/s int16 recordings
+(BASELINE.json metric), one process per GPU.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
 
-One "step" = one pass of the hot path over one recording (BASELINE.json configs[2]: 60 s of 25 MS/s int16 IQ,
---chunk-seconds): PCPS acquisition of 32 PRNs (+-5 kHz / 250 Hz, 1 ms x 10) on the first 10 ms, hand-off on
-the device, closed-loop E/P/L tracking of the 12 acquired channels over the whole recording.  `--lanes` steps are kept in flight
-(ColdStartPool): the 12-channel tracking launch is a latency chain on part of the GPU, the
-acquisition of the next chunk runs beside it.  Weak scaling: every rank owns one recording
-(seed 1003 + rank); the only collective is the NCCL all-gather of the 24-byte peak records.
-`value` is timed with the chunks resident in HBM; `e2e` goes through the public calls
-(ColdStartPool.submit_host / result) from pinned host memory, H2D and D2H of every epoch record
-inside the timed region; `e2e.from_file` is the same workload from an IQ file (StreamingReceiver).
+One "step" = one pass of the hot path over one batch of input: `--recordings` (24) recordings of BASELINE.json
+configs[2] (60 s of 25 MS/s int16 IQ each, --chunk-seconds) resident in HBM, every one in its own memory.  Per recording:
+PCPS acquisition of 32 PRNs (+-5 kHz / 250 Hz, 1 ms x 10) on the first 10 ms and the hand-off on the device; then ONE
+tracking launch closes the loops of all 24 x 12 channels over the whole minute (ColdStartBatch; PACK instantiation of
+K-TRK, two channels per SM).  Weak scaling: every rank owns its own batch (seeds derived from the rank); no data-path
+collective -- the acquisition peak tables are all-gathered over NCCL once per K steps and checked.
+`value` is timed with the batch resident in HBM; `e2e` goes through the public one-recording calls
+(ColdStartPool.submit_host / result) from pinned host memory, H2D and D2H of every epoch record inside the timed
+region (PCIe-bound); `e2e.from_file` is the same workload from an IQ file (StreamingReceiver); `single_stream` is one
+recording alone on the GPU with the latency shape of K-TRK.
 """
 from __future__ import annotations
 
@@ -27,6 +28,9 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# the end-to-end leg keeps 5 recordings x 3 streams in flight: more hardware queues than the default 8, so that independent
+# streams do not serialise behind each other (read when the CUDA context is created)
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 
 FS = 25e6
 NBITS = 16
@@ -39,18 +43,19 @@ FLOP_PER_SAMPLE_CH = 31.0
 NCU_TRAFFIC_FILE = "profiles/ncu_traffic.json"
 
 
-def ncu_traffic(chunk_seconds):
+def ncu_traffic(chunk_seconds, recordings=24):
     """(DRAM bytes per step of the dominant launches, description) from NCU_TRAFFIC_FILE, or (None, why)."""
     try:
         t = json.load(open(os.path.join(ROOT, NCU_TRAFFIC_FILE)))
         trk, ifft, fwd = t["trk_borre_kernel"], t["acq_ifft_kernel"], t["acq_fwd_kernel"]
-        total = trk["dram_bytes"] * (chunk_seconds / trk["chunk_seconds"]) + ifft["dram_bytes"] + fwd["dram_bytes"]
+        trk_bytes = trk["dram_bytes"] * (chunk_seconds / trk["chunk_seconds"]) * (recordings / trk["recordings"])
+        total = trk_bytes + recordings * (ifft["dram_bytes"] + fwd["dram_bytes"])
         return total, {"file": NCU_TRAFFIC_FILE, "measured_in_this_run": False,
-                       "trk_borre_kernel": trk["dram_bytes"] * (chunk_seconds / trk["chunk_seconds"]),
-                       "acq_ifft_kernel": ifft["dram_bytes"], "acq_fwd_kernel": fwd["dram_bytes"],
+                       "trk_borre_kernel": trk_bytes, "acq_ifft_kernel": ifft["dram_bytes"], "acq_fwd_kernel": fwd["dram_bytes"],
                        "sources": sorted({trk["source"], ifft["source"], fwd["source"]}),
-                       "note": f"ncu captures of an earlier run of this workload (not this run); the tracking launch was captured on a "
-                               f"{trk['chunk_seconds']:g} s chunk and is scaled to {chunk_seconds:g} s (its traffic is the samples, read once)"}
+                       "note": f"ncu captures of an earlier run of this workload (not this run); the tracking launch was captured on "
+                               f"{trk['recordings']} recordings of {trk['chunk_seconds']:g} s and is scaled to {recordings} x {chunk_seconds:g} s "
+                               "(its traffic is the samples, read once per recording, plus the records); the acquisition kernels per recording"}
     except Exception as exc:
         return None, {"file": NCU_TRAFFIC_FILE, "error": f"{type(exc).__name__}: {exc}"}
 
@@ -229,6 +234,50 @@ def make_recording(rank, chunk_s, device):
     return sc, host
 
 
+def fill_batch(batch, sc0, host, rank, args, dev):
+    """The B recordings of a rank, back to back in the batch's device buffer: `--seeds` of them are generated (slot 0 is the
+    rank's recording `host`, seed 1003 + rank; the others have their own satellites' Dopplers, delays, noise), the rest
+    are those multiplied by j, -1 and -j -- other samples in other memory, the same satellites with the carrier phase
+    turned by a quarter / half / three quarters of a cycle.  Returns the scenario (truth) of every slot."""
+    import torch
+    from sydr_b200 import synth
+    B, S = batch.B, max(1, min(args.seeds, batch.B))
+    scs = [None] * B
+    dwell = 2 * batch.acq.required_samples
+    j = 0
+    for i in range(S):
+        if i == 0:
+            sc = sc0
+            batch.slot(0).copy_(host, non_blocking=True)
+        else:
+            while True:                    # a constant 12 channels per recording: a draw whose cold start misses a satellite is skipped
+                j += 1
+                sc = synth.make_scenario(FS, NBITS, args.chunk_seconds, synth.PRNS_12, 2003 + 16 * j + rank, 250.0)
+                batch.slot(i).copy_(synth.generate_iq_torch(sc, device=dev))
+                pk = batch.acq.run(batch.slot(i)[:dwell])["peaks"]
+                if sorted(int(p["prn"]) for p in pk if p["ratio"] > batch.threshold) == sorted(s_.prn for s_ in sc.sats):
+                    break
+                if j > 4 * S + 8:
+                    raise SystemExit("fill_batch: no synthetic recording with all its satellites acquired")
+        scs[i] = sc
+    for r in range(S, B):
+        src, dst = batch.slot(r % S).view(-1, 2), batch.slot(r).view(-1, 2)
+        k = (r // S) % 4
+        if k == 0:
+            dst.copy_(src)
+        elif k == 1:
+            dst[:, 0] = -src[:, 1]
+            dst[:, 1] = src[:, 0]
+        elif k == 2:
+            torch.neg(src, out=dst)
+        else:
+            dst[:, 0] = src[:, 1]
+            dst[:, 1] = -src[:, 0]
+        scs[r] = scs[r % S]
+    torch.cuda.synchronize()
+    return scs
+
+
 def run_reference(args, rank, world):
     """--impl reference: the reference algorithm of the path on this box's host cores (the oracle port: the
     Python reference itself cannot travel to the GPU box, and bench.py never reads /root/reference).  Same
@@ -287,7 +336,10 @@ def run_reference(args, rank, world):
     base["rtf"] = chunk_samples / FS / step_s
     line = {"impl": "reference", "metric": "cold acquisition (32 PRN) + 12-channel tracking throughput", "value": v,
             "unit": "Msamples/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": step_s * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": step_s * 1e3, "recordings_per_step": 1,
+            "step_note": f"a step of this arm is ONE recording (the bounded sample of the GPU arm's step of {args.recordings} recordings: the host "
+                         "cores work through recordings one after the other, so Msamples/s does not depend on how many a step holds)",
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic", "rtf": chunk_samples / FS / step_s,
             "sampled": bool(base["sampled"]), "timed_s": timed, "run_s": time.perf_counter() - t_run,
             "timed_note": "timed_s = wall clock of the K timed steps as executed; ms_per_step = the step scaled to the whole "
@@ -532,15 +584,16 @@ def kaplan_variant(dev, d_iq, sc, chunk_seconds, chunk_samples):
 
 
 def workload_config(args, world):
-    return {"workload": f"cfg3-format recording per GPU (25 MS/s int16 IQ, 12 PRNs @45 dB-Hz, {args.chunk_seconds:g} s chunk "
-                        "per step): 32-PRN PCPS acquisition (+-5 kHz/250 Hz, 1 ms x 10) + 12-channel closed-loop E/P/L tracking",
+    B = getattr(args, "recordings", 24)
+    return {"workload": f"{B} cfg3-format recordings per GPU and step (25 MS/s int16 IQ, 12 PRNs @45 dB-Hz, {args.chunk_seconds:g} s each): "
+                        "per recording 32-PRN PCPS acquisition (+-5 kHz/250 Hz, 1 ms x 10) + device hand-off, then 12-channel closed-loop "
+                        f"E/P/L tracking of all {B} recordings by one launch",
             "fs_hz": FS, "iq": "int16", "chunk_seconds": args.chunk_seconds, "search_prns": 32, "channels": N_CHANNELS,
-            "recordings": world, "parallelism": f"recording-per-gpu x{world}, {getattr(args, 'lanes', 1)} steps in flight per GPU",
-            "lanes": getattr(args, "lanes", 1),
-            "l2": f"input chunk {args.chunk_seconds * FS * 4 / 1e6:.0f} MB per step exceeds the 126 MB L2",
-            "e2e_call": "ColdStartPipeline.process_host(pinned int16 IQ): H2D in 4 pieces on a copy stream, acquisition, "
-                        "device hand-off, tracking behind the upload, D2H of peak table and all epoch records into a ring "
-                        "of pinned result buffers (returned as views)"}
+            "recordings_per_gpu": B, "recordings": B * world, "generated_recordings_per_gpu": min(getattr(args, "seeds", 6), B),
+            "parallelism": f"recordings-per-gpu x{world}: {B} recordings side by side in one tracking launch per GPU, no data-path collective "
+                           "(the acquisition peak tables are all-gathered once per K steps)",
+            "l2": f"input {B} x {args.chunk_seconds * FS * 4 / 1e6:.0f} MB per step, every recording in its own memory, exceeds the 126 MB L2",
+            "e2e_call": "ColdStartPool.submit_host / result, one recording per call from pinned host memory (see e2e.call)"}
 
 
 def main():
@@ -554,7 +607,10 @@ def main():
                          "fine acquisition sweep split over the GPUs")
     ap.add_argument("--chunk-seconds", type=float, default=60.0,
                     help="length of the recording a step processes (BASELINE.json configs[2]: 60 s)")
-    ap.add_argument("--lanes", type=int, default=5, help="steps in flight per GPU (ColdStartPool)")
+    ap.add_argument("--recordings", type=int, default=24,
+                    help="recordings per step and GPU, tracked by one launch (ColdStartBatch): 24 x 12 channels = two CTAs on each of 144 SMs")
+    ap.add_argument("--seeds", type=int, default=6, help="recordings of a batch that are generated; the others are these times j, -1, -j")
+    ap.add_argument("--lanes", type=int, default=5, help="end-to-end leg: recordings in flight per GPU (ColdStartPool)")
     ap.add_argument("--cluster", type=int, default=0)
     ap.add_argument("--threads", type=int, default=0)
     ap.add_argument("--no-tma", action="store_true")
@@ -577,7 +633,7 @@ def main():
     import torch
     import torch.distributed as dist
     from sydr_b200 import _lib as L
-    from sydr_b200.pipeline import ColdStartPool
+    from sydr_b200.pipeline import ColdStartBatch, ColdStartPipeline, ColdStartPool
 
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
@@ -598,60 +654,17 @@ def main():
             dist.destroy_process_group()
         return
 
+    B = args.recordings
     sc, host = make_recording(rank, args.chunk_seconds, dev)
     chunk_samples = host.numel() // 2
-    # `lanes` steps in flight: the acquisition of step k+1 runs beside the tracking of step k, which is a
-    # latency chain on 96 of the 148 SMs (ColdStartPool)
-    pool = ColdStartPool(lanes=args.lanes, fs=FS, nbits=NBITS, search_prns=SEARCH_PRNS, n_channels=N_CHANNELS,
-                         max_seconds=args.chunk_seconds, device=dev, cluster=args.cluster, threads=args.threads,
-                         use_tma=not args.no_tma, **ACQ)
-    pipe = pool.lanes[0]
-    d_iq = pipe.upload(host)
-    torch.cuda.synchronize()
-    # The acquisition peak tables (768 B per step and rank) are all-gathered over NCCL in ONE collective per K steps: every
-    # step snapshots its table on the lane's side stream into a history buffer, the collective follows the last step.
-    # (One collective per step, enqueued while five tracking launches fill the SMs, stalled the enqueueing host thread
+    truth = {s.prn: s.doppler for s in sc.sats}
+    # The acquisition peak tables (768 B per recording) are all-gathered over NCCL in ONE collective per K steps: every
+    # step copies its tables in stream order into a history buffer, the collective follows the last step.
+    # (One collective per step, enqueued while tracking launches fill the SMs, stalled the enqueueing host thread
     # for ~6 ms per step on 2 GPUs: profiles/r2/bench_2gpu_allgather_per_step.json.)
     PEAK_BYTES = len(SEARCH_PRNS) * 24
     comm = torch.cuda.Stream(device=dev) if world > 1 else None
-    peaks_hist = torch.zeros(max(args.steps, args.warmup, 2) * PEAK_BYTES, dtype=torch.uint8, device=dev) if world > 1 else None
-    gathered = torch.empty(world * peaks_hist.numel(), dtype=torch.uint8, device=dev) if world > 1 else None
     step_no = [0]
-
-    def peaks_slot():
-        """Where this step's peak table goes (None on one GPU): the pipeline copies it there in stream order, right
-        behind the acquisition."""
-        if world == 1 or args.no_gather:
-            return None
-        k = step_no[0] % (peaks_hist.numel() // PEAK_BYTES)
-        step_no[0] += 1
-        return peaks_hist[k * PEAK_BYTES:(k + 1) * PEAK_BYTES]
-
-    def gather_peaks():
-        if world > 1 and not args.no_gather:
-            for lane in range(args.lanes):
-                comm.wait_stream(pool.stream(lane))
-            with torch.cuda.stream(comm):
-                dist.all_gather_into_tensor(gathered, peaks_hist)
-
-    def run_steps(n, submit, records, marks_out=None):
-        """n steps with at most `lanes` in flight; results collected in order."""
-        tickets = []
-        for _ in range(n):
-            if len(tickets) == args.lanes:
-                pool.result(tickets.pop(0), records=records)
-            marks = [] if marks_out is not None else None
-            t = submit(marks)
-            tickets.append(t)
-            if marks_out is not None:
-                marks_out.append(marks)
-        gather_peaks()
-        while tickets:
-            pool.result(tickets.pop(0), records=records)
-
-    def step_e2e():
-        out = pipe.process_host(host)
-        return out
 
     def barrier():
         torch.cuda.synchronize()
@@ -659,28 +672,118 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    # ================= end to end first (its upload buffers are given back before the batch takes the HBM) =================
+    # `lanes` recordings in flight (ColdStartPool): each lane uploads its recording in pieces on a copy stream, acquires on
+    # the first 10 ms, hands off on the device and tracks behind the upload with the latency shape of K-TRK (the path is
+    # PCIe-bound: 6 GB per recording at ~55 GB/s), D2H of the peak table and of every epoch record inside the timed region.
+    pool = ColdStartPool(lanes=args.lanes, fs=FS, nbits=NBITS, search_prns=SEARCH_PRNS, n_channels=N_CHANNELS,
+                         max_seconds=args.chunk_seconds, device=dev, cluster=args.cluster, threads=args.threads,
+                         use_tma=not args.no_tma, **ACQ)
+    pipe = pool.lanes[0]
+    e2e_hist = torch.zeros(max(args.steps, 2) * PEAK_BYTES, dtype=torch.uint8, device=dev) if world > 1 else None
+
+    def e2e_slot():
+        if world == 1 or args.no_gather:
+            return None
+        k = step_no[0] % (e2e_hist.numel() // PEAK_BYTES)
+        step_no[0] += 1
+        return e2e_hist[k * PEAK_BYTES:(k + 1) * PEAK_BYTES]
+
+    def run_pool_steps(n):
+        """n recordings end to end with at most `lanes` in flight; results collected in order."""
+        tickets = []
+        for _ in range(n):
+            if len(tickets) == args.lanes:
+                pool.result(tickets.pop(0), records=True)
+            tickets.append(pool.submit_host(host, peaks_out=e2e_slot()))
+        while tickets:
+            pool.result(tickets.pop(0), records=True)
+
     # ---- correctness gate on this very input: tracked Dopplers must match the generator's truth
-    out = step_e2e()
+    out = pipe.process_host(host)
     torch.cuda.synchronize()
-    truth = {s.prn: s.doppler for s in sc.sats}
     # the loop output jitters by a few Hz epoch to epoch at 45 dB-Hz: gate on the mean of the last 200 epochs
     got = {c["prn"]: float(np.mean(e["carrier_freq"][-200:])) for c, e in zip(out["channels"], out["epochs"])}
     bad = [p for p in truth if p not in got or abs(got[p] - truth[p]) > 5.0]
     if bad or min(len(e) for e in out["epochs"]) < int(args.chunk_seconds * 1000) - 12:
         raise SystemExit(f"rank {rank}: tracking did not converge to the synthetic truth for PRNs {bad}")
     d2h_bytes = len(SEARCH_PRNS) * 24 + sum(e.nbytes for e in out["epochs"]) + 4 * len(out["epochs"])
-
-    # ---- warm-up, then K steps resident in HBM
-    run_steps(args.warmup, lambda m: pool.submit_device(d_iq, m, peaks_slot()), False)
+    n_ch = len(out["channels"])
+    host_np = host.numpy()
+    cpu_channels = out["channels"]
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()                                 # (NVML start-up takes milliseconds: before the barrier); rank 0's GPU only
+    run_pool_steps(2)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    run_pool_steps(args.steps)
+    barrier()
+    e1.record()
+    torch.cuda.synchronize()
+    ms_e2e = e0.elapsed_time(e1)
+    e2e_steps = args.steps
+    pool.close()
+    for p_ in pool.lanes:
+        p_._d_iq_buf = None
+    del pool, pipe, out
+    torch.cuda.empty_cache()
+
+    # ================= device-resident: B recordings per step, ONE tracking launch (ColdStartBatch) =================
+    batch = ColdStartBatch(B, fs=FS, nbits=NBITS, search_prns=SEARCH_PRNS, n_channels=N_CHANNELS, max_seconds=args.chunk_seconds,
+                           device=dev, **ACQ)
+    scs = fill_batch(batch, sc, host, rank, args, dev)
+    d_iq = batch.slot(0)
+    torch.cuda.synchronize()
+    peaks_hist = torch.zeros(max(args.steps, args.warmup, 2) * B * PEAK_BYTES, dtype=torch.uint8, device=dev) if world > 1 else None
+    gathered = torch.empty(world * peaks_hist.numel(), dtype=torch.uint8, device=dev) if world > 1 else None
+    step_no[0] = 0
+
+    def peaks_slot():
+        """Where this step's B peak tables go (None on one GPU): copied there in stream order, behind the acquisitions."""
+        if world == 1 or args.no_gather:
+            return None
+        k = step_no[0] % (peaks_hist.numel() // (B * PEAK_BYTES))
+        step_no[0] += 1
+        return peaks_hist[k * B * PEAK_BYTES:(k + 1) * B * PEAK_BYTES]
+
+    def gather_peaks():
+        if world > 1 and not args.no_gather:
+            comm.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(comm):
+                dist.all_gather_into_tensor(gathered, peaks_hist)
+
+    def run_steps(n, marks_out=None):
+        ctx = None
+        for _ in range(n):
+            marks = [] if marks_out is not None else None
+            ctx = batch.enqueue(marks=marks, peaks_out=peaks_slot())
+            if marks_out is not None:
+                marks_out.append(marks)
+        gather_peaks()
+        return ctx
+
+    # ---- gate on every recording of the batch: 12 channels each, all epochs, tracked Dopplers at the generator's truth
+    ctx = run_steps(1)
+    res0 = batch.finish(ctx, records=False)
+    nep, status, prn_of, fmean = batch.device_summary(200)
+    for r in range(B):
+        tr = {s.prn: s.doppler for s in scs[r].sats}
+        sl = slice(r * N_CHANNELS, (r + 1) * N_CHANNELS)
+        found = [c["prn"] for c in res0[r]["channels"]]
+        badb = [int(p) for p, f in zip(prn_of[sl], fmean[sl]) if int(p) not in tr or abs(f - tr[int(p)]) > 5.0]
+        if found != sorted(tr) or badb or (status[sl] != 0).any() or nep[sl].min() < int(args.chunk_seconds * 1000) - 12:
+            raise SystemExit(f"rank {rank}: recording {r} of the batch: channels {found}, off the truth {badb}, status {status[sl].tolist()}, epochs {nep[sl].min()}")
+
+    # ---- warm-up, then K steps resident in HBM
+    run_steps(args.warmup)
     lib.sydr_reset_launch_count()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
     k_ev = []
     barrier()                                           # every rank enters the timed region together
     ev[0].record()
-    run_steps(args.steps, lambda m: pool.submit_device(d_iq, m, peaks_slot()), False, k_ev)
+    run_steps(args.steps, k_ev)
     torch.cuda.synchronize()
     ev[2].record()                                      # this rank's own steps are done (diagnostics: per_rank_ms)
     barrier()
@@ -689,44 +792,47 @@ def main():
     ms_own = ev[0].elapsed_time(ev[2])
     launches = int(lib.sydr_launch_count())
     ms_dev = ev[0].elapsed_time(ev[1])
-    ms_acq = float(np.mean([m[0].elapsed_time(m[1]) for m in k_ev]))
-    ms_trk = float(np.mean([m[2].elapsed_time(m[3]) for m in k_ev]))
+    ms_acq = float(np.mean([m[0].elapsed_time(m[1]) for m in k_ev]))           # B acquisitions + hand-offs
+    ms_trk = float(np.mean([m[2].elapsed_time(m[3]) for m in k_ev]))           # the one tracking launch
+    clocks = sampler.stop() if rank == 0 else None
 
-    # ---- the two kernels timed alone (one step in flight), for the per-kernel figures
-    alone = []
-    for _ in range(4):
-        m = []
-        pipe.process_device(d_iq, m)
-        torch.cuda.synchronize()
-        alone.append(m)
-    ms_acq_alone = float(np.mean([m[0].elapsed_time(m[1]) for m in alone[1:]]))
-    ms_trk_alone = float(np.mean([m[2].elapsed_time(m[3]) for m in alone[1:]]))
+    # ---- the gathered peak tables of the timed steps are read: every rank's B x 32 records, 12 satellites found on each
+    gathered_ok = None
+    if world > 1 and not args.no_gather:
+        comm.synchronize()
+        from sydr_b200 import _lib as _L
+        n_hist = peaks_hist.numel() // (B * PEAK_BYTES)
+        g = gathered.cpu().numpy().view(_L.ACQ_PEAK_DTYPE).reshape(world, n_hist, B, len(SEARCH_PRNS))[:, :min(args.steps, n_hist)]
+        gathered_ok = bool(((g["ratio"] > 1.5).sum(axis=-1) == N_CHANNELS).all() and (g["prn"] == np.array(SEARCH_PRNS)).all())
+        if not gathered_ok:
+            raise SystemExit(f"rank {rank}: the all-gathered peak tables are not the ranks' acquisition results")
 
-    # ---- one recording on its own, as a single stream would run it: the latency instantiation of K-TRK (the pool's DENSE
-    # instantiation trades a few per cent of a lone launch for packing several launches on the GPU)
+    # ---- one recording through the one-recording pipeline (latency shape), for the per-kernel figures of a lone recording
+    pipe = ColdStartPipeline(fs=FS, nbits=NBITS, search_prns=SEARCH_PRNS, n_channels=N_CHANNELS, max_seconds=args.chunk_seconds,
+                             device=dev, cluster=args.cluster, threads=args.threads, use_tma=not args.no_tma, dense=False, **ACQ)
+    # ---- one recording on its own, as a single stream would run it: the latency instantiation of K-TRK (cluster of 8 CTAs
+    # per channel), acquisition, hand-off, then its serial chain of epochs; first launch to last
     single = None
-    if world == 1:
-        try:
-            from sydr_b200.pipeline import ColdStartPipeline
-            sp = ColdStartPipeline(fs=FS, nbits=NBITS, search_prns=SEARCH_PRNS, n_channels=N_CHANNELS, max_seconds=args.chunk_seconds,
-                                   device=dev, cluster=args.cluster, threads=args.threads, use_tma=not args.no_tma, dense=False, **ACQ)
-            ss = []
-            for _ in range(4):
-                m = []
-                sp.process_device(d_iq, m)
-                torch.cuda.synchronize()
-                ss.append((m[0].elapsed_time(m[1]), m[2].elapsed_time(m[3]), m[0].elapsed_time(m[3])))
-            so = sp.finish(sp.enqueue_device(d_iq), records=True)
-            sgot = {c["prn"]: float(np.mean(e["carrier_freq"][-200:])) for c, e in zip(so["channels"], so["epochs"])}
-            sp.close()
-            if any(abs(sgot[p] - truth[p]) > 5.0 for p in truth):
-                raise SystemExit("single-stream run did not converge")
-            a_ms, t_ms, all_ms = (float(np.mean([x[i] for x in ss[1:]])) for i in range(3))
-            single = {"acq_ms": a_ms, "trk_ms": t_ms, "step_ms": all_ms, "us_per_epoch": t_ms * 1e3 / (chunk_samples / (FS * 1e-3)),
-                      "rtf": args.chunk_seconds * 1e3 / all_ms, "tflops": FLOP_PER_SAMPLE_CH * chunk_samples * N_CHANNELS / (t_ms * 1e-3) / 1e12,
-                      "kernel": "trk_borre_kernel, latency instantiation (cluster of 8 CTAs per channel, one step in flight)"}
-        except (Exception, SystemExit) as exc:
-            single = {"error": f"{type(exc).__name__}: {exc}"}
+    ms_acq_alone = ms_trk_alone = float("nan")
+    try:
+        ss = []
+        for _ in range(4):
+            m = []
+            pipe.process_device(d_iq, m)
+            torch.cuda.synchronize()
+            ss.append((m[0].elapsed_time(m[1]), m[2].elapsed_time(m[3]), m[0].elapsed_time(m[3])))
+        so = pipe.finish(pipe.enqueue_device(d_iq), records=True)
+        sgot = {c["prn"]: float(np.mean(e["carrier_freq"][-200:])) for c, e in zip(so["channels"], so["epochs"])}
+        if any(abs(sgot[p] - truth[p]) > 5.0 for p in truth):
+            raise SystemExit("single-stream run did not converge")
+        del so
+        ms_acq_alone, ms_trk_alone, all_ms = (float(np.mean([x[i] for x in ss[1:]])) for i in range(3))
+        single = {"acq_ms": ms_acq_alone, "trk_ms": ms_trk_alone, "step_ms": all_ms,
+                  "us_per_epoch": ms_trk_alone * 1e3 / (chunk_samples / (FS * 1e-3)),
+                  "rtf": args.chunk_seconds * 1e3 / all_ms, "tflops": FLOP_PER_SAMPLE_CH * chunk_samples * N_CHANNELS / (ms_trk_alone * 1e-3) / 1e12,
+                  "kernel": "trk_borre_kernel, latency instantiation (cluster of 8 CTAs per channel, one recording on the GPU)"}
+    except (Exception, SystemExit) as exc:
+        single = {"error": f"{type(exc).__name__}: {exc}"}
 
     # ---- cuFFT timed comparison of the acquisition sweep (north star: "cuFFT serves only as a timed comparison")
     cufft = None
@@ -737,37 +843,18 @@ def main():
         except (Exception, SystemExit) as exc:
             cufft = {"error": f"{type(exc).__name__}: {exc}"}
 
-    # ---- the Kaplan loop closure on the same chunk, one step in flight
+    # ---- the Kaplan loop closure on the same recording, alone on the GPU
     kap = None
     if world == 1 and not args.no_kaplan:
         try:                                            # an optional section must not cost the headline line
             kap = kaplan_variant(dev, d_iq, sc, args.chunk_seconds, chunk_samples)
         except (Exception, SystemExit) as exc:
             kap = {"error": f"{type(exc).__name__}: {exc}"}
-
-    # ---- K steps end to end from pinned host memory
-    run_steps(2, lambda m: pool.submit_host(host, peaks_out=peaks_slot()), True)
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    run_steps(args.steps, lambda m: pool.submit_host(host, peaks_out=peaks_slot()), True)
-    barrier()
-    e1.record()
-    torch.cuda.synchronize()
-    ms_e2e = e0.elapsed_time(e1)
-    clocks = sampler.stop() if rank == 0 else None
-
-    # ---- the gathered peak tables of the last steps are read: every rank's 32 records, 12 satellites found on each
-    gathered_ok = None
-    if world > 1 and not args.no_gather:
-        comm.synchronize()
-        from sydr_b200 import _lib as _L
-        n_hist = peaks_hist.numel() // PEAK_BYTES
-        g = gathered.cpu().numpy().view(_L.ACQ_PEAK_DTYPE).reshape(world, n_hist, len(SEARCH_PRNS))[:, :min(args.steps, n_hist)]
-        gathered_ok = bool(all(int((g[r, k]["ratio"] > 1.5).sum()) == N_CHANNELS and (g[r, k]["prn"] == np.array(SEARCH_PRNS)).all()
-                               for r in range(world) for k in range(g.shape[1])))
-        if not gathered_ok:
-            raise SystemExit(f"rank {rank}: the all-gathered peak tables are not the ranks' acquisition results")
+    pipe.close()
+    batch.close()
+    batch.release()
+    del batch, d_iq, pipe
+    torch.cuda.empty_cache()
 
     # ---- the other sharded path: configs[3]'s acquisition cells split over the ranks, real all-gather
     acq_split = None
@@ -786,9 +873,9 @@ def main():
         per_rank = allr
     ms_dev, ms_e2e = float(t[0]), float(t[1])
     per_rank_ms = [round(float(v), 3) for v in per_rank.cpu()]
-    total_samples = float(chunk_samples) * world * args.steps
+    total_samples = float(chunk_samples) * B * world * args.steps
     value = total_samples / (ms_dev * 1e-3) / 1e6
-    e2e = total_samples / (ms_e2e * 1e-3) / 1e6
+    e2e = float(chunk_samples) * world * e2e_steps / (ms_e2e * 1e-3) / 1e6
 
     if rank == 0:
         peaks_file = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -798,51 +885,50 @@ def main():
         import ctypes as C
         tfv, clkv = C.c_double(), C.c_double()
         L.check(lib.sydr_measure_fp32_peak(C.byref(tfv), C.byref(clkv)))
-        n_ch = len(out["channels"])
-        trk_flop = FLOP_PER_SAMPLE_CH * chunk_samples * n_ch
-        trk_bytes = 4.0 * chunk_samples + 128.0 * n_ch * (chunk_samples / (FS * 1e-3))
+        n_epochs = chunk_samples / (FS * 1e-3)
+        trk_flop = FLOP_PER_SAMPLE_CH * chunk_samples * n_ch * B                     # the one tracking launch of a step
+        trk_flop_one = FLOP_PER_SAMPLE_CH * chunk_samples * n_ch
+        trk_bytes = (4.0 * chunk_samples + 128.0 * n_ch * n_epochs) * B
         n_code = int(FS * 1e-3)
-        acq_flop = len(SEARCH_PRNS) * 41 * ACQ["coh"] * ACQ["noncoh"] * f_acq(n_code)
-        # With several steps in flight the launches of different steps overlap on the GPU, so a launch's
-        # duration on its own stream is no longer the time the GPU spends on it.  The physically meaningful
-        # figure over the timed region is the aggregate: algorithmic flops of the K steps / the time they took.
-        # The per-kernel figures (inside the region and alone) are listed under "kernels".
+        acq_flop_one = len(SEARCH_PRNS) * 41 * ACQ["coh"] * ACQ["noncoh"] * f_acq(n_code)
+        acq_flop = acq_flop_one * B
         step_flop = trk_flop + acq_flop
         step_ms = ms_dev / args.steps                              # step period of one GPU (roofline is per GPU)
         ach = step_flop / (step_ms * 1e-3) / 1e12
-        dominant = "trk_borre_kernel" if ms_trk_alone >= ms_acq_alone else "acq_ifft_kernel"
-        traffic, traffic_info = ncu_traffic(args.chunk_seconds)
-        ach_dom_alone = (trk_flop / (ms_trk_alone * 1e-3) / 1e12) if dominant == "trk_borre_kernel" else (acq_flop / (ms_acq_alone * 1e-3) / 1e12)
-        ach_dom_in = (trk_flop / (ms_trk * 1e-3) / 1e12) if dominant == "trk_borre_kernel" else (acq_flop / (ms_acq * 1e-3) / 1e12)
-        # roofline.achieved / frac = the DOMINANT KERNEL on its own (algorithmic flops of one launch / its duration with one
-        # step in flight); the aggregate over the overlapped steps of the timed region is reported next to it.
-        roofline = {"kernel": f"{dominant} (12 channels, one launch, one step in flight)" if dominant == "trk_borre_kernel" else dominant,
-                    "bound": "fp32", "achieved": ach_dom_alone, "peak": tfv.value, "unit": "TFLOP/s",
-                    "frac": ach_dom_alone / tfv.value if tfv.value else None,
-                    "achieved_in_region": ach_dom_in, "frac_in_region": ach_dom_in / tfv.value if tfv.value else None,
+        traffic, traffic_info = ncu_traffic(args.chunk_seconds, B)
+        ach_trk = trk_flop / (ms_trk * 1e-3) / 1e12
+        # roofline.achieved / frac = the DOMINANT KERNEL: the tracking launch of a step (one launch, B x 12 channels), algorithmic
+        # flops / its duration inside the timed region (CUDA events on its stream; the launches of a step follow each other
+        # on one stream, nothing else shares the GPU).
+        roofline = {"kernel": f"trk_borre_kernel, PACK instantiation ({B} recordings x {n_ch} channels = {B * n_ch} CTAs in one launch, two per SM)",
+                    "bound": "fp32", "achieved": ach_trk, "peak": tfv.value, "unit": "TFLOP/s",
+                    "frac": ach_trk / tfv.value if tfv.value else None,
+                    "share_of_step": ms_trk / step_ms,
                     "aggregate_achieved": ach, "aggregate_frac": ach / tfv.value if tfv.value else None,
-                    "aggregate_note": f"algorithmic flops of acq_fwd + acq_ifft + trk_borre of the K steps / the timed region ({args.lanes} independent "
-                                      "steps in flight): throughput of several jobs sharing the GPU, not one kernel's roofline fraction",
-                    "traffic": traffic, "traffic_source": traffic_info, "algorithmic_bytes_per_step": trk_bytes,
+                    "aggregate_note": "algorithmic flops of every launch of the K steps (B acquisitions + the tracking launch each) / the timed region",
+                    "traffic": traffic, "traffic_source": traffic_info, "algorithmic_bytes_per_launch": trk_bytes,
                     "definition": "achieved = algorithmic flops per launch (31 flop x samples x channels, SURVEY.md 8d) / average launch "
-                                  "duration (CUDA events on the launching stream)",
+                                  "duration over the timed region (CUDA events on the launching stream)",
                     "peak_source": f"FP32 FMA chain measured in this run ({clkv.value:.0f} MHz max clock)",
-                    "note": "12 channels occupy <= 96 of 148 SMs and every channel is a serial chain of 1 ms epochs: "
-                            "the bound of one launch is per-epoch latency, not the FP32 or HBM roof (DESIGN.md §4); several "
-                            "steps are kept in flight so that other launches use the SMs and issue slots it leaves idle",
+                    "note": "every channel is a serial chain of 1 ms epochs (correlate -> all-reduce -> FP64 loop closure -> next epoch's NCO): "
+                            "the launch is bound by instruction issue (65 % busy, ALU pipe 44 %, FMA 33 %: profiles/r2/pack_brief.txt), "
+                            "not by HBM; two channels per SM overlap one's loop closure with the other's correlation",
                     "hbm": {"achieved": trk_bytes / (ms_trk * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                             "frac": trk_bytes / (ms_trk * 1e-3) / 1e9 / hbm_peak, "peak_source": hbm_src},
-                    "kernels": {"trk_borre_kernel": {"ms": ms_trk, "tflops": trk_flop / (ms_trk * 1e-3) / 1e12,
-                                                     "us_per_epoch": ms_trk * 1e3 / (chunk_samples / (FS * 1e-3)),
-                                                     "alone_ms": ms_trk_alone,
-                                                     "alone_us_per_epoch": ms_trk_alone * 1e3 / (chunk_samples / (FS * 1e-3)),
-                                                     "alone_tflops": trk_flop / (ms_trk_alone * 1e-3) / 1e12},
-                                "acq (fwd+ifft+reduce)": {"ms": ms_acq, "tflops": acq_flop / (ms_acq * 1e-3) / 1e12,
+                    "kernels": {"trk_borre_kernel (PACK, the step's launch)": {
+                                    "ms": ms_trk, "tflops": ach_trk, "channels": B * n_ch,
+                                    "us_per_epoch_all_channels": ms_trk * 1e3 / n_epochs,
+                                    "us_per_recording_epoch": ms_trk * 1e3 / n_epochs / B},
+                                "trk_borre_kernel (latency instantiation, one recording alone)": {
+                                    "alone_ms": ms_trk_alone, "alone_us_per_epoch": ms_trk_alone * 1e3 / n_epochs,
+                                    "alone_tflops": trk_flop_one / (ms_trk_alone * 1e-3) / 1e12,
+                                    "alone_frac": trk_flop_one / (ms_trk_alone * 1e-3) / 1e12 / tfv.value if tfv.value else None},
+                                "acq (fwd+ifft+reduce)": {"ms_per_step": ms_acq, "ms": ms_acq / B, "tflops": acq_flop / (ms_acq * 1e-3) / 1e12,
+                                                          "per_step": f"{B} acquisitions + device hand-offs per step, one after the other",
                                                           "alone_ms": ms_acq_alone,
-                                                          "alone_tflops": acq_flop / (ms_acq_alone * 1e-3) / 1e12}},
-                    "kernels_note": f"ms = launch duration inside the timed region ({args.lanes} steps in flight: the "
-                                    "acquisition of one step shares the GPU with the tracking of another); alone_ms = the "
-                                    "same launch with one step in flight"}
+                                                          "alone_tflops": acq_flop_one / (ms_acq_alone * 1e-3) / 1e12}},
+                    "kernels_note": "ms = launch duration inside the timed region (the launches of a step run one after the other); "
+                                    "alone_* = one recording through ColdStartPipeline with nothing else on the GPU"}
         if kap is not None:
             roofline["kernels"]["kaplan_variant"] = kap
         if cufft is not None:
@@ -857,16 +943,21 @@ def main():
         line = {"metric": "cold acquisition (32 PRN) + 12-channel tracking throughput", "value": value, "unit": "Msamples/s",
                 "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev / args.steps,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "rtf": value * 1e6 / FS / world, "jobs_in_flight": args.lanes,
-                "rtf_single_stream": (single["rtf"] if single and "rtf" in single else args.chunk_seconds * 1e3 / (ms_acq_alone + ms_trk_alone)),
+                "rtf": value * 1e6 / FS / world, "recordings_per_step": B,
+                "rtf_single_stream": (single["rtf"] if single and "rtf" in single else None),
                 "single_stream": single,
-                "rtf_note": f"rtf = aggregate of {args.lanes} independent cold-start jobs in flight per GPU; rtf_single_stream = one recording "
-                            "alone (acquisition, hand-off, then its serial chain of tracking epochs; first launch to last, CUDA events)",
+                "rtf_note": f"rtf = seconds of signal processed per second per GPU: {B} recordings are tracked side by side by one launch "
+                            f"(each recording on its own advances at rtf / {B}); rtf_single_stream = one recording alone on the GPU with the "
+                            "latency shape (acquisition, hand-off, then its serial chain of tracking epochs; first launch to last, CUDA events)",
                 "config": workload_config(args, world), "clocks": clocks,
                 "e2e": {"value": e2e, "unit": "Msamples/s", "rtf": e2e * 1e6 / FS / world,
-                        "h2d_bytes_per_step": int(host.numel() * host.element_size()), "d2h_bytes_per_step": int(d2h_bytes)},
+                        "h2d_bytes_per_step": int(host.numel() * host.element_size()), "d2h_bytes_per_step": int(d2h_bytes),
+                        "steps": e2e_steps, "step": "one recording (6 GB up, all epoch records down)", "recordings_in_flight": args.lanes,
+                        "call": "ColdStartPool.submit_host(pinned int16 IQ) / result(): H2D in 4 pieces on a copy stream, acquisition, device "
+                                "hand-off, tracking behind the upload (latency shape), D2H of the peak table and of all epoch records into a "
+                                "ring of pinned result buffers (returned as views)"},
                 "gpu_launches": launches, "per_rank_ms": per_rank_ms,
-                "per_rank_note": "each rank's own K steps (device time up to its last result), before the closing barrier; the line's "
+                "per_rank_note": "each rank's own K steps (device time up to its last launch), before the closing barrier; the line's "
                                  "ms_per_step is the region between the two barriers, max over ranks",
                 "roofline": roofline}
         if acq_split is not None:
@@ -879,7 +970,7 @@ def main():
                 line["e2e"]["from_file"] = {"error": f"{type(exc).__name__}: {exc}"}
         if world == 1 and not args.no_cpu_baseline:
             try:
-                line["cpu_baseline"] = cpu_baseline(host.numpy(), out["channels"], chunk_samples)
+                line["cpu_baseline"] = cpu_baseline(host_np, cpu_channels, chunk_samples)
             except Exception as exc:
                 line["cpu_baseline"] = {"error": f"{type(exc).__name__}: {exc}", "kind": "port"}
         print(json.dumps(line))

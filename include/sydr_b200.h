@@ -196,7 +196,11 @@ typedef struct {
                                records' `start` stay recording-relative (streaming ingest)   */
     int32_t use_iq_base;
     int32_t dense;          /* 1 = register-lean instantiation of the latency kernel (3 CTAs per SM): a few
-                               per cent slower alone, denser when several launches share the GPU    */
+                               per cent slower alone, denser when several launches share the GPU;
+                               2 = PACK, the throughput shape of the staged kernel (with cluster = 1, use_tma = 1,
+                               integer IQ whose 1 ms window fits 108 KB): one CTA and ONE staged window per
+                               channel, two channels per SM, one's loop closure under the other's correlation
+                               (falls back to 1 where the shape does not apply)                        */
     int32_t kernel;         /* 0 = automatic; 1 = prefix-moment kernel (throughput shape: the samples of a recording are
                                turned into prefix moments once, every channel gathers from them; int16 IQ, Borre loops);
                                2 = per-channel kernels only                                          */
@@ -251,7 +255,8 @@ int sydr_convert_to_f32(const void* d_in, int iq_dtype, long long n_samples, flo
  * states ordered by PRN: carrierFrequency = IF - (-range + step * freq_idx), currentSample =
  * current_sample + required_samples - track_required + code_idx + 1; every other member is
  * copied from *d_template (loop coefficients, spacings, code NCO at nominal, see
- * sydr_trk_state_init).  Slots beyond the selected count are marked idle (status 1).
+ * sydr_trk_state_init; iq_base too: a template per recording places its channels at the recording's
+ * offset inside the buffer of a many-recording tracking launch).  Slots beyond the selected count are marked idle (status 1).
  * d_n_selected (may be NULL) receives the count.  No host synchronisation. */
 int sydr_acq_handoff(const sydr_acq_peak* d_peaks, int n_prn, double inter_freq, double doppler_range,
                      double doppler_step, long long required_samples, long long track_required,

@@ -230,7 +230,7 @@ __global__ void __launch_bounds__(64) acq_handoff_kernel(const sydr_acq_peak* __
         st.prn = pk.prn;
         st.carrier_freq = __dadd_rn(inter_freq, doppler);                                                  // L303
         st.cur = current_sample + required - track_required + (long long)pk.code_idx + 1;                  // L306-311
-        st.iq_base = 0;
+        // (iq_base stays the template's: where this recording lies inside the tracking launch's buffer, ColdStartBatch)
         st.iq_len = iq_len;
         st.epochs_done = 0;
         st.status = 0;

@@ -111,10 +111,16 @@ __global__ void __launch_bounds__(256) epl_batch_kernel(const uint8_t* __restric
 // machine) instead of the Borre PLL; the code loop and everything else are shared.
 // DENSE = same code under a tighter register budget (two CTAs of 288 threads per SM guaranteed, three of 192
 // in practice): 4 % slower alone, but launches of several steps in flight pack 3 per SM instead of 2.
-template <int DT, int VPC, bool TMA, bool LEAN, bool PROF = false, bool KAP = false, bool DENSE = false>
-__global__ void __launch_bounds__(LEAN ? kLeanThreads : (KAP ? kKaplanMaxThreads : (DENSE ? kDenseMaxThreads : kTrkMaxThreads)),
-                                  LEAN ? 3 : (DENSE ? 2 : 1))
+// PACK = throughput shape of the staged kernel (cfg.dense = 2): one CTA per channel with ONE staged window instead of
+// two, so that two CTAs (two channels) share an SM and one channel's serial section -- gather, totals, FP64 loop closure,
+// next epoch's constants: 40 % of an epoch for a CTA alone on its SM -- runs under the other's correlation.  The window
+// of epoch k+1 is requested by the last warp as soon as every warp has released the window of epoch k (mbarrier), and
+// lands while warps 0 / 1 close the loops.
+template <int DT, int VPC, bool TMA, bool LEAN, bool PROF = false, bool KAP = false, bool DENSE = false, bool PACK = false>
+__global__ void __launch_bounds__(LEAN ? kLeanThreads : (KAP ? kKaplanMaxThreads : (PACK ? kPackThreads : (DENSE ? kDenseMaxThreads : kTrkMaxThreads))),
+                                  LEAN ? 3 : ((DENSE || PACK) ? 2 : 1))
 trk_borre_kernel(const TrkParams P) {
+    static_assert(!PACK || (TMA && !LEAN && !PROF && !KAP), "PACK is an instantiation of the staged Borre kernel");
     constexpr int SPV = IqTraits<DT>::SPV, BPS = IqTraits<DT>::BPS;
     constexpr int C = SPV * VPC;
     extern __shared__ __align__(128) uint8_t dyn_smem[];
@@ -123,7 +129,7 @@ trk_borre_kernel(const TrkParams P) {
     // (one REDUX per component instead of a shuffle tree, 32 B instead of 64 B per warp and CTA,
     // order-independent integer totals).  complex64 input has no bound: FP32 tree + FP64 totals.
     constexpr bool FIX = (DT != SYDR_IQ_F32);
-    __shared__ __align__(16) TrkSharedT<(LEAN ? kLeanThreads / 32 : kMaxCluster * kTrkMaxWarps), (NV > 0 ? kSegTab : 1)> sh;
+    __shared__ __align__(16) TrkSharedT<(LEAN ? kLeanThreads / 32 : (PACK ? kPackThreads / 32 : kMaxCluster * kTrkMaxWarps)), (NV > 0 ? kSegTab : 1)> sh;
     const unsigned full = 0xffffffffu;
 
     const uint32_t S = cluster_nctarank();
@@ -161,6 +167,7 @@ trk_borre_kernel(const TrkParams P) {
         // cluster: one arrival (expect_tx) + S*W*64 bytes of st.async; single CTA: one arrival per warp
         mbar_init(&sh.bar_gather[0], S > 1 ? 1u : (uint32_t)W);
         mbar_init(&sh.bar_gather[1], S > 1 ? 1u : (uint32_t)W);
+        mbar_init(&sh.bar_free, (uint32_t)W);       // PACK: one arrival per warp that has finished reading the window
         fence_mbar_init();
     }
     __syncthreads();
@@ -297,7 +304,7 @@ trk_borre_kernel(const TrkParams P) {
         if (sh.ctl.stop) break;
         SYDR_TICK(1)                                   // barrier (waits for the slower closing warp)
 
-        const int buf = epoch & 1;
+        const int buf = PACK ? 0 : (epoch & 1);
         const long long a = sh.ctl.a;
         const long long a0 = a & ~(long long)(SPV - 1);
         const int lead = (int)(a - a0);
@@ -305,14 +312,14 @@ trk_borre_kernel(const TrkParams P) {
         const int n_epoch = sh.ctl.ec.n;
         if (TMA && warp == W - 1 && lane == 0) {
             if (epoch == 0) trk_prefetch<DT, VPC>(sh, dyn_smem, rec_base, rec_alloc, a, rank, Q, 0);
-            // next epoch's window, fetched while this one is correlated
-            trk_prefetch<DT, VPC>(sh, dyn_smem + (size_t)(buf ^ 1) * win_bytes, rec_base, rec_alloc, a + n_epoch, rank, Q, buf ^ 1);
+            // next epoch's window, fetched while this one is correlated (PACK: behind the correlation, below)
+            if (!PACK) trk_prefetch<DT, VPC>(sh, dyn_smem + (size_t)(buf ^ 1) * win_bytes, rec_base, rec_alloc, a + n_epoch, rank, Q, buf ^ 1);
         }
 
         // ---- (B) correlate this CTA's window
         float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         int err = 0;
-        if (TMA) mbar_wait(&sh.bar_data[buf], (epoch >> 1) & 1);
+        if (TMA) mbar_wait(&sh.bar_data[buf], PACK ? (epoch & 1) : ((epoch >> 1) & 1));
         SYDR_TICK(2)                                   // wait for the staged window
         if (NV > 0 && LEAN) {
             correlate_rounds<(NV > 0 ? NV : 1)>(rec_base + a * BPS, sh.ctl.ec.rounds, sh.ctl.ec, sh.rot, sh.segtab, sh.seg_q,
@@ -378,6 +385,15 @@ trk_borre_kernel(const TrkParams P) {
             }
         }
         SYDR_TICK(4)                                   // warp reduction + send
+        if (PACK) {
+            // the single window: every warp releases it, the last warp refills it with the next epoch's samples
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sh.bar_free);
+            if (warp == W - 1 && lane == 0) {
+                mbar_wait(&sh.bar_free, epoch & 1);
+                trk_prefetch<DT, VPC>(sh, dyn_smem, rec_base, rec_alloc, a + n_epoch, rank, Q, 0);
+            }
+        }
         const int e = epoch;
         ++epoch;
         // ---- (C) close the loops of epoch e
@@ -407,7 +423,7 @@ trk_borre_kernel(const TrkParams P) {
     }
 
     // the window of the epoch that will not run was already requested: drain it before exit
-    if (TMA && epoch > 0) mbar_wait(&sh.bar_data[epoch & 1], (epoch >> 1) & 1);
+    if (TMA && epoch > 0) mbar_wait(&sh.bar_data[PACK ? 0 : (epoch & 1)], PACK ? (epoch & 1) : ((epoch >> 1) & 1));
 
     if (warp == 0 && lane == 0) sh.sc = sc;
     if (warp == 1 && lane == 0) sh.sk = sk;
@@ -457,7 +473,7 @@ int launch_epl(const void* d_iq, long long iq_len, double fs, const sydr_epl_arg
 template <int DT, int VPC>
 int launch_trk(const TrkParams& P, int n_channels, int cluster, int threads, int lean, cudaStream_t s) {
     constexpr int C = IqTraits<DT>::SPV * VPC;
-    const size_t smem = P.use_tma ? (size_t)2 * (P.Q * C + kWinTail) * IqTraits<DT>::BPS : 0;
+    const size_t smem = P.use_tma ? (size_t)(P.dense == 2 ? 1 : 2) * (P.Q * C + kWinTail) * IqTraits<DT>::BPS : 0;
     SYDR_REQUIRE(smem <= 200 * 1024, SYDR_ERR_UNSUPPORTED,
                  "tracking window needs %zu B of shared memory; raise cfg.cluster", smem);
     constexpr bool HAS_LEAN = SegTraits<DT, VPC>::NV > 0;
@@ -468,6 +484,9 @@ int launch_trk(const TrkParams& P, int n_channels, int cluster, int threads, int
                          : trk_borre_kernel<DT, VPC, false, false, false, false, true>;
     if (P.kstates != nullptr)
         kern = P.use_tma ? trk_borre_kernel<DT, VPC, true, false, false, true> : trk_borre_kernel<DT, VPC, false, false, false, true>;
+    if constexpr (DT != SYDR_IQ_F32) {
+        if (P.dense == 2) kern = trk_borre_kernel<DT, VPC, true, false, false, false, false, true>;     // (trk_run_impl checked the shape)
+    }
     size_t smem_launch = smem;
     if constexpr (HAS_LEAN) {
         if (lean) {
@@ -625,8 +644,23 @@ static int trk_run_impl(const void* d_iq, int iq_dtype, long long iq_alloc_sampl
     const double gap = (cfg && cfg->min_tap_gap > 0.0) ? cfg->min_tap_gap : 0.5;
     const int vpc = pick_vpc(iq_dtype, fs, gap);
     const int C = spv * vpc;
+    // PACK (cfg.dense = 2): one CTA per channel, one window, two CTAs per SM -- when the window leaves room for that
+    const long long win1 = ((n_max + spv + (long long)C - 1) / C * C + kWinTail) * bps;
+    const bool auto_shape = !cfg || cfg->cluster <= 0;
+    const bool staged_ok = cluster == 1 && use_tma && iq_dtype != SYDR_IQ_F32 && d_kstates == nullptr && g_trk_prof == nullptr;
+    bool pack = cfg && cfg->dense == 2 && staged_ok && win1 <= kPackWindowBytes && (threads <= 0 || threads <= kPackThreads);
+    // Automatic throughput shapes (more channels than clusters of two fit: cluster = 1), measured at 25 MS/s int16 on one
+    // B200 (profiles/r2/pack_shapes.txt), SM time per channel-epoch: staged kernel, one CTA of 384 threads per SM 3.75 us
+    // (<= 148 channels); PACK, two CTAs per SM 3.1 us (<= 296 channels); LEAN, three CTAs per SM 4.0 us (beyond).
+    bool staged_one = false;
+    if (auto_shape && staged_ok && !(cfg && cfg->kernel == 1) && threads <= 0) {
+        if (n_channels <= 148 && 2 * win1 <= 200 * 1024) staged_one = true;
+        else if (n_channels <= 296 && win1 <= kPackWindowBytes) pack = true;
+    }
+    if (pack && threads <= 0) threads = kPackThreads;
+    if (staged_one) threads = kTrkMaxThreads;
     // shared-memory budget: two windows of Q*C samples
-    while (use_tma && cluster < 8 && 2 * (((n_max + spv + (long long)C * cluster - 1) / ((long long)C * cluster)) * C + kWinTail) * bps > 200 * 1024)
+    while (!pack && use_tma && cluster < 8 && 2 * (((n_max + spv + (long long)C * cluster - 1) / ((long long)C * cluster)) * C + kWinTail) * bps > 200 * 1024)
         cluster <<= 1;                                     // (the chunk size chosen above is kept)
     const int Q = (int)((n_max + spv + (long long)C * cluster - 1) / ((long long)C * cluster));
     if (threads <= 0) {
@@ -650,8 +684,7 @@ static int trk_run_impl(const void* d_iq, int iq_dtype, long long iq_alloc_sampl
     if (iq_dtype == SYDR_IQ_I16) nv = (vpc == 1) ? 3 : (vpc == 3) ? 7 : (vpc == 5) ? 13 : 0;
     const double half_chip = 0.5 * fs / kCodeFreq;
     const bool seg_fits = nv > 0 && g_trk_mode == 0 && half_chip >= 2 * nv - 2 + 0.05 && half_chip <= 2 * nv - 1 - 0.05;
-    const bool auto_shape = !cfg || cfg->cluster <= 0;
-    const bool lean = d_kstates == nullptr && seg_fits && ((auto_shape && cluster == 1) ||
+    const bool lean = !pack && !staged_one && d_kstates == nullptr && seg_fits && ((auto_shape && cluster == 1) ||
                                    (!auto_shape && cluster == 1 && !use_tma && threads > 0 && threads <= kLeanThreads &&
                                     (threads & (threads - 1)) == 0));   // power of two: rounds by shift
 
@@ -687,7 +720,7 @@ static int trk_run_impl(const void* d_iq, int iq_dtype, long long iq_alloc_sampl
     P.prof = g_trk_prof;
     P.kstates = d_kstates;
     P.kout = d_kout;
-    P.dense = cfg ? (cfg->dense != 0) : 0;
+    P.dense = pack ? 2 : (cfg ? (cfg->dense != 0) : 0);
     cudaStream_t s = (cudaStream_t)stream;
     // Prefix-moment kernel (trkm.cu): the per-sample work done once per recording (int16 IQ) -- only on request
     // (cfg.kernel = 1): measured slower than the LEAN instantiation on this GPU, so the automatic

@@ -771,7 +771,7 @@ struct TrkParams {
     double acc_inv;          // 1 / acc_scale
     int resume;              // follow-up of a LEAN launch: continue the record rows, serve kNeedGeneral channels
     long long* prof;         // optional [n_channels][16] phase cycle counters of thread 0 (NULL = off)
-    int dense;               // DENSE instantiation requested (steps in flight share the GPU)
+    int dense;               // 1: DENSE instantiation requested (steps in flight share the GPU); 2: PACK
     sydr_kaplan_state* kstates;   // Kaplan loop closure (KAP instantiation): per-channel state and per-epoch extras
     sydr_kaplan_epoch* kout;
 };
@@ -787,6 +787,8 @@ constexpr int kWinTail = 32;     // samples staged beyond a CTA's window (segmen
 constexpr int kTrkMaxThreads = 384;
 constexpr int kDenseMaxThreads = 288;    // DENSE instantiation: <= 113 registers, three CTAs per SM beside other launches
 constexpr int kLeanThreads = 256;
+constexpr int kPackThreads = 320;        // PACK instantiation: two CTAs per SM under 102 registers
+constexpr int kPackWindowBytes = 108 * 1024;   // its single window: what two CTAs per SM leave of 227 KB beside 5 KB of static shared memory
 constexpr int kKaplanMaxThreads = 384;   // the Kaplan carrier warp holds more state: 170 registers per thread instead of 102
 constexpr int kNeedGeneral = 2;  // channel status: stopped in front of an epoch only the general kernel serves
 
@@ -800,6 +802,7 @@ struct TrkSharedT {          // static shared memory of the closed-loop kernel
     alignas(16) double gather[2][NE][8];
     alignas(8) uint64_t bar_data[2];
     uint64_t bar_gather[2];
+    uint64_t bar_free;       // PACK: the staged window has been read by every warp
     float2 rot[kRotMax];     // throughput loop: carrier rotation between a lane's consecutive windows
     sydr_trk_state cfgs;     // the channel's state as loaded (constants live here)
     CodeState sc;            // owned by warp 0

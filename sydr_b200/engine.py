@@ -232,20 +232,21 @@ class TrackingEngine:
         self.max_epochs = int(max_epochs)
         st = np.ascontiguousarray(states)
         assert st.dtype == L.TRK_STATE_DTYPE
+        # dense: 0 / False = latency instantiation, 1 / True = DENSE (several launches share the GPU), 2 = PACK (throughput
+        # shape of the staged kernel: with cluster = 1, one CTA and one staged window per channel, two channels per SM)
         # kernel: 0 = automatic, 1 = prefix-moment kernel (throughput shape, `group` channels of a recording per CTA),
         # 2 = per-channel kernels only
         self.cfg = L.TrkConfig(int(cluster), int(threads), 1 if use_tma else 0, 0, 0, min_tap_gap(st["spacing"]), 0, 0,
-                               1 if dense else 0, int(kernel), int(group), _rec_channels(st["iq_base"]), 0)
+                               int(dense), int(kernel), int(group), _rec_channels(st["iq_base"]), 0)
         self._states = torch.from_numpy(st.view(np.uint8).reshape(-1).copy()).to(self.device)
         self._out = torch.empty(self.n_ch * self.max_epochs * 128, dtype=torch.uint8, device=self.device)
         self._nep = torch.zeros(self.n_ch, dtype=torch.int32, device=self.device)
         # pinned staging for the results: one asynchronous D2H per fetch, no pageable bounce.  A ring of
         # buffers, so that fetch(copy=False) can hand out views that survive the next fetches.
+        # (allocated on first use: a launch whose records stay on the device never pins host memory for them)
         self.RING = 4
-        self._out_ring = [torch.empty(self.n_ch * self.max_epochs * 128, dtype=torch.uint8, pin_memory=True)
-                          for _ in range(self.RING)]
+        self._out_ring = [None] * self.RING
         self._ring_i = 0
-        self._out_host = self._out_ring[0]
         self._nep_host = torch.zeros(self.n_ch, dtype=torch.int32, pin_memory=True)
 
     def set_iq_len(self, iq_len):
@@ -287,6 +288,8 @@ class TrackingEngine:
         views of pinned staging memory (no host copy, no page faults: ~1 ms saved per 3 MB); they stay
         valid until RING - 1 further fetches of this engine."""
         self._ring_i = (self._ring_i + 1) % self.RING
+        if self._out_ring[self._ring_i] is None:
+            self._out_ring[self._ring_i] = torch.empty(self.n_ch * self.max_epochs * 128, dtype=torch.uint8, pin_memory=True)
         self._out_host = self._out_ring[self._ring_i]
         self._nep_host.copy_(self._nep, non_blocking=True)
         self._out_host.copy_(self._out, non_blocking=True)

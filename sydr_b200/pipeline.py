@@ -44,7 +44,8 @@ class ColdStartPipeline:
         self.max_epochs = int(math.ceil(max_seconds * 1000.0)) + 8
         self._tdt = torch.int8 if nbits == 8 else torch.int16
         pad = IQ_PAD_BYTES // (1 if nbits == 8 else 2)
-        self._d_iq = torch.zeros(2 * self.max_samples + pad, dtype=self._tdt, device=self.device)
+        self._iq_elems = 2 * self.max_samples + pad
+        self._d_iq_buf = None                                     # upload buffer, allocated on first use (device-resident callers never need it)
         self._copy_stream = torch.cuda.Stream(device=self.device)
         self._side_stream = torch.cuda.Stream(device=self.device)
         # Hand-off on the device (K-HAND): a template state with the loop coefficients, the tracking
@@ -77,6 +78,12 @@ class ColdStartPipeline:
 
     def close(self):
         self.acq.close()
+
+    @property
+    def _d_iq(self) -> torch.Tensor:
+        if self._d_iq_buf is None:
+            self._d_iq_buf = torch.zeros(self._iq_elems, dtype=self._tdt, device=self.device)
+        return self._d_iq_buf
 
     # ---- stages --------------------------------------------------------------------------
     def device_buffer(self, n_samples: int) -> torch.Tensor:
@@ -282,3 +289,137 @@ class ColdStartPool:
         """The lane's side stream: ordered behind its acquisition (peak table complete), not behind its
         tracking.  Where a multi-GPU caller enqueues the all-gather of the 768-byte peak table."""
         return self.lanes[lane]._side_stream
+
+
+class ColdStartBatch:
+    """B recordings per step, tracked by ONE launch (throughput shape; BASELINE.json configs[4] with the cold start of
+    configs[2] in front): the recordings lie back to back in one device buffer (`stride` int8/int16 elements apart, see
+    slot()); a step enqueues, on one stream, acquisition + device hand-off (K-HAND) of every recording -- each hand-off
+    writes the recording's n_channels states with iq_base at its slot -- and then a single tracking launch over all
+    B x n_channels channels with the PACK instantiation of K-TRK (cfg.dense = 2: one CTA and one staged window per channel,
+    two channels per SM, so that one channel's serial loop closure runs under the other's correlation).  148 SMs hold
+    296 channels: 24 recordings of 12 channels per launch.  Per-recording results equal ColdStartPipeline's to the
+    summation-order tolerance of the correlator sums.  Replaces the per-channel processes of
+    sydr/receiver/receiver.py:120-139 / sydr/channel/channelManager.py:149-188 for many recordings at once."""
+
+    def __init__(self, recordings, fs, nbits, search_prns, n_channels, doppler_range=5000.0, doppler_step=250.0, coh=1,
+                 noncoh=10, max_seconds=2.0, inter_freq=0.0, threshold=1.5, channel_cfg=None, device=None,
+                 cluster=1, threads=0, use_tma=True, dense=2):
+        L.require_device()
+        if device is not None:
+            torch.cuda.set_device(device)
+        self.device = torch.device("cuda", torch.cuda.current_device())
+        self.B, self.n_channels = int(recordings), int(n_channels)
+        self.fs, self.nbits, self.threshold = float(fs), int(nbits), float(threshold)
+        self.acq = AcquisitionEngine(fs, inter_freq, doppler_range, doppler_step, coh, noncoh, list(search_prns), device=self.device)
+        self.max_samples = int(round(max_seconds * fs))
+        self.max_epochs = int(math.ceil(max_seconds * 1000.0)) + 8
+        self._tdt = torch.int8 if nbits == 8 else torch.int16
+        pad = IQ_PAD_BYTES // (1 if nbits == 8 else 2)
+        self.stride = (2 * self.max_samples + pad + 15) // 16 * 16       # elements between recordings (iq_base: a multiple of 8 samples)
+        tmpl = make_trk_states(self.fs, [dict(prn=1, carrier_freq=0.0, start_sample=0)], channel_cfg)
+        tmpls = np.repeat(tmpl, self.B)
+        tmpls["iq_base"] = np.arange(self.B, dtype=np.int64) * (self.stride // 2)
+        self._tmpls = torch.from_numpy(tmpls.view(np.uint8).reshape(self.B, -1).copy()).to(self.device)
+        idle = np.repeat(tmpls, self.n_channels)
+        idle["status"] = 1
+        self._trk = TrackingEngine(self.fs, idle, self.max_epochs, device=self.device, cluster=cluster, threads=threads,
+                                   use_tma=use_tma, dense=dense)
+        self._state_bytes = tmpl.dtype.itemsize
+        self._n_sel = torch.zeros(self.B, dtype=torch.int32, device=self.device)
+        self._peak_bytes = len(self.acq.prns) * 24
+        self._peaks_dev = torch.zeros(self.B * self._peak_bytes, dtype=torch.uint8, device=self.device)
+        self._peaks_host = torch.empty(self.B * self._peak_bytes, dtype=torch.uint8, pin_memory=True)
+        self._track_required = int(math.ceil(CODE_CHIPS / (CODE_FREQ / self.fs)))
+        self._side_stream = torch.cuda.Stream(device=self.device)
+        self._buf = None
+
+    def close(self):
+        self.acq.close()
+
+    def buffer(self) -> torch.Tensor:
+        """The device buffer of the B recordings (allocated on first use)."""
+        if self._buf is None:
+            # (the storage extends IQ_PAD_BYTES past the last recording: the tracking launch takes the view as it is)
+            pad = IQ_PAD_BYTES // (1 if self.nbits == 8 else 2)
+            self._store = torch.zeros(self.B * self.stride + pad, dtype=self._tdt, device=self.device)
+            self._buf = self._store[:self.B * self.stride]
+        return self._buf
+
+    def release(self):
+        """Give the device buffer of the recordings back (it is allocated again on the next buffer() / slot())."""
+        self._buf = self._store = None
+
+    def slot(self, r: int, n_samples: int | None = None) -> torch.Tensor:
+        """Where recording r lives: interleaved I/Q elements [r * stride, r * stride + 2 n)."""
+        n = self.max_samples if n_samples is None else int(n_samples)
+        if n > self.max_samples:
+            raise L.SydrError("recording longer than max_seconds")
+        return self.buffer()[r * self.stride:r * self.stride + 2 * n]
+
+    def enqueue(self, n_samples: int | None = None, marks: list | None = None, peaks_out: torch.Tensor | None = None) -> dict:
+        """Enqueue one step over the recordings resident in buffer() on the current stream: B x (acquisition, hand-off),
+        then one tracking launch.  `marks` receives four timing events: before / after the acquisitions + hand-offs,
+        before / after the tracking launch.  Nothing here waits for the GPU."""
+        n = self.max_samples if n_samples is None else int(n_samples)
+        a, lib = self.acq, L.load()
+        cur = torch.cuda.current_stream()
+        mark = (lambda: marks.append(_mark())) if marks is not None else (lambda: None)
+        buf = self.buffer()
+        mark()
+        for r in range(self.B):
+            a.launch(buf[r * self.stride:r * self.stride + 2 * a.required_samples])
+            self._peaks_dev[r * self._peak_bytes:(r + 1) * self._peak_bytes].copy_(a.peaks_device(), non_blocking=True)
+            L.check(lib.sydr_acq_handoff(a.peaks_device().data_ptr(), len(a.prns), a.inter_freq, a.doppler_range,
+                                         a.doppler_step, a.required_samples, self._track_required, 0, self.threshold,
+                                         self._tmpls[r].data_ptr(), n,
+                                         self._trk._states.data_ptr() + r * self.n_channels * self._state_bytes,
+                                         self.n_channels, self._n_sel[r:].data_ptr(), cur.cuda_stream), "sydr_acq_handoff")
+        if peaks_out is not None:          # a device copy of the step's B peak tables for the caller (multi-GPU: what the all-gather sends)
+            peaks_out.copy_(self._peaks_dev, non_blocking=True)
+        mark()
+        ev = torch.cuda.Event()
+        ev.record(cur)
+        self._side_stream.wait_event(ev)
+        with torch.cuda.stream(self._side_stream):                 # the peak tables travel behind the acquisitions only
+            self._peaks_host.copy_(self._peaks_dev, non_blocking=True)
+            got = torch.cuda.Event()
+            got.record(self._side_stream)
+        mark()
+        self._trk.launch(buf)
+        mark()
+        return dict(got=got, n=n)
+
+    def finish(self, ctx: dict, records: bool = False, copy: bool = False) -> list:
+        """Host side of a step: per recording the peak table, the channel list and (records=True) the per-epoch
+        tracking records of its channels."""
+        ctx["got"].synchronize()
+        peaks = self._peaks_host.numpy().view(L.ACQ_PEAK_DTYPE).reshape(self.B, -1).copy()
+        recs = self._trk.fetch(copy=copy) if records else None
+        out = []
+        for r in range(self.B):
+            order = np.argsort(-peaks[r]["ratio"], kind="stable")
+            sel = sorted([i for i in order if peaks[r]["ratio"][i] > self.threshold][:self.n_channels], key=lambda i: int(peaks[r]["prn"][i]))
+            chans = []
+            for i in sel:
+                carrier, _, start = self.acq.handoff(peaks[r][i])
+                chans.append(dict(prn=int(peaks[r]["prn"][i]), carrier_freq=carrier, start_sample=start, iq_len=ctx["n"], rec=r))
+            o = dict(peaks=peaks[r], channels=chans)
+            if records:
+                o["epochs"] = recs[r * self.n_channels:r * self.n_channels + len(chans)]
+            out.append(o)
+        return out
+
+    def device_summary(self, last: int = 200):
+        """Without moving the records to the host: per channel slot the epochs tracked, the status and the mean carrier
+        frequency over its last `last` epochs (what a lock / truth check needs), reduced on the device."""
+        nep = self._trk._nep.to(torch.int64)
+        rows = self._trk._out.view(torch.float64).view(self._trk.n_ch, self.max_epochs, 16)[:, :, 8]      # carrier_freq
+        k = torch.arange(self.max_epochs, device=self.device)[None, :]
+        m = (k < nep[:, None]) & (k >= (nep[:, None] - last))
+        mean = torch.where(m, rows, torch.zeros((), dtype=rows.dtype, device=self.device)).sum(dim=1) / m.sum(dim=1).clamp(min=1)
+        st = self._trk.states()
+        return nep.cpu().numpy(), st["status"].copy(), st["prn"].copy(), mean.cpu().numpy()
+
+    def process(self, n_samples: int | None = None, records: bool = True, copy: bool = True) -> list:
+        return self.finish(self.enqueue(n_samples), records=records, copy=copy)

@@ -30,11 +30,11 @@ def test_reference_arm_line():
 def test_tracked_traffic_file():
     sys.path.insert(0, H.ROOT)
     import bench
-    total, info = bench.ncu_traffic(60.0)
+    total, info = bench.ncu_traffic(60.0, 24)
     assert info["file"] == "profiles/ncu_traffic.json" and info["measured_in_this_run"] is False
-    assert os.path.exists(os.path.join(H.ROOT, info["sources"][0]))
-    # the tracking launch reads its samples once: 4 B x 25 MS/s x 60 s, plus the records
-    assert 0.98 * 6.0e9 < info["trk_borre_kernel"] < 1.1 * 6.0e9 and total > info["trk_borre_kernel"]
+    assert all(os.path.exists(os.path.join(H.ROOT, src)) for src in info["sources"])
+    # the tracking launch of a step reads the samples of its 24 recordings once: 24 x 4 B x 25 MS/s x 60 s, plus the records
+    assert 0.98 * 24 * 6.0e9 < info["trk_borre_kernel"] < 1.1 * 24 * 6.0e9 and total > info["trk_borre_kernel"]
 
 
 def test_legacy_prototypes_cover_the_header():

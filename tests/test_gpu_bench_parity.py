@@ -132,7 +132,62 @@ def test_headline_chunk_dense_pool_vs_oracle():
 
 
 SHAPES = {"cta_per_channel": dict(cluster=1, threads=256, use_tma=False, kernel=2),      # LEAN instantiation of trk.cu
+          "pack": dict(cluster=1, threads=0, use_tma=True, dense=2),                     # PACK instantiation (ColdStartBatch, bench.py's timed launch)
           "moments_g3": dict(kernel=1, group=3), "moments_g4": dict(kernel=1, group=4), "moments_g1": dict(kernel=1, group=1)}
+
+
+def test_batch_step_vs_pipeline_and_oracle():
+    """bench.py's timed step: ColdStartBatch -- B recordings (distinct seeds) back to back in one buffer, B acquisitions
+    and device hand-offs, ONE tracking launch of B x 12 channels with the PACK instantiation.  Every recording against
+    (1) ColdStartPipeline on the same samples (same peak table, same channels, same epoch boundaries, loop outputs within
+    the north-star tolerances) and (2) the oracle, teacher-forced and closed loop."""
+    import torch
+    from sydr_b200 import synth
+    from sydr_b200.pipeline import ColdStartBatch, ColdStartPipeline
+    B, chunk_s = 3, 1.0
+    kw = dict(fs=FS, nbits=16, search_prns=list(range(1, 33)), n_channels=12, max_seconds=chunk_s,
+              doppler_range=5000.0, doppler_step=250.0, coh=1, noncoh=10)
+    batch = ColdStartBatch(B, **kw)
+    xs = []
+    for r in range(B):
+        sc = synth.make_scenario(FS, 16, chunk_s, synth.PRNS_12, 1103 + r, 250.0)
+        batch.slot(r).copy_(synth.generate_iq_torch(sc, device="cuda"))
+        xs.append(to_c64(batch.slot(r).cpu().numpy()))
+    torch.cuda.synchronize()
+    outs = batch.process(records=True, copy=True)
+    st = batch._trk.states()
+    assert (st["status"] == 0).all()
+    again = batch.process(records=True, copy=True)              # a second step over the same buffer: the same bits
+    pipe = ColdStartPipeline(**kw)
+    chans, recs = [], []
+    for r, (o, o2) in enumerate(zip(outs, again)):
+        assert [c["prn"] for c in o["channels"]] == list(synth.PRNS_12)
+        assert o["peaks"].tobytes() == o2["peaks"].tobytes()
+        for a, b in zip(o["epochs"], o2["epochs"]):
+            assert a.tobytes() == b.tobytes()
+        ref = pipe.finish(pipe.enqueue_device(batch.slot(r)), records=True, copy=True)
+        assert ref["peaks"].tobytes() == o["peaks"].tobytes()
+        for c, cr, e, er in zip(o["channels"], ref["channels"], o["epochs"], ref["epochs"]):
+            assert (c["prn"], c["carrier_freq"], c["start_sample"]) == (cr["prn"], cr["carrier_freq"], cr["start_sample"])
+            n = min(len(e), len(er))
+            assert n >= 985 and abs(len(e) - len(er)) <= 1
+            # (two closed loops whose partial sums are added in different orders: an epoch boundary may fall one sample
+            # apart where the code phase sits within 1e-9 of a sample instant; the absolute code phase is what must agree)
+            ph = lambda t: ((t["start"][:n] + t["n"][:n]) - t["rem_code"][:n] / (t["code_freq"][:n] / FS)) * (1.023e6 / FS)
+            assert np.abs(ph(e) - ph(er)).max() <= TOL_CHIP
+            assert np.abs(e["start"][:n] - er["start"][:n]).max() <= 1
+            assert np.abs(e["carrier_freq"][:n] - er["carrier_freq"][:n]).max() <= TOL_HZ
+            assert np.abs(e["code_freq"][:n] - er["code_freq"][:n]).max() <= TOL_HZ
+            # (two closed loops with different partial-sum orders: their carrier phases differ by milliradians, which turns
+            # I into Q by as much -- the 1e-4 correlator tolerance is checked teacher-forced against the oracle below)
+            scale = np.hypot(er["corr"][:n, 2], er["corr"][:n, 3])[:, None]
+            assert (np.abs(e["corr"][:n] - er["corr"][:n]) / scale).max() <= 2e-2
+        chans += o["channels"]
+        recs += o["epochs"]
+    pipe.close()
+    batch.close()
+    res = check_against_oracle(xs, chans, recs)
+    print("batch step vs oracle:", {k: max(r[k] for r in res) for k in ("e_corr", "e_state", "d_car", "d_code", "d_phase")})
 
 
 @pytest.mark.parametrize("shape", list(SHAPES))

@@ -135,12 +135,14 @@ CONFIGS = [dict(cluster=1, threads=0, use_tma=True), dict(cluster=2, threads=0, 
            dict(cluster=1, threads=256, use_tma=False), dict(cluster=8, threads=64, use_tma=False),
            # the DENSE instantiation bench.py's timed region launches (ColdStartPool, several steps in flight)
            dict(cluster=0, threads=0, use_tma=True, dense=True), dict(cluster=8, threads=160, use_tma=True, dense=True),
+           # the PACK instantiation (cfg.dense = 2: one CTA per channel, one staged window, two CTAs per SM) of ColdStartBatch
+           dict(cluster=1, threads=0, use_tma=True, dense=2), dict(cluster=1, threads=128, use_tma=True, dense=2),
            # the prefix-moment kernel (trkm.cu; int16 IQ only: at fs4 / int8 it must hand every channel to the general kernel)
            dict(cluster=0, threads=0, use_tma=True, kernel=1, group=1), dict(cluster=0, threads=0, use_tma=True, kernel=1, group=2)]
 
 
 @pytest.mark.parametrize("name", ["fs4", "fs25"])
-@pytest.mark.parametrize("cfg", CONFIGS, ids=lambda c: f"S{c['cluster']}T{c['threads']}{'tma' if c['use_tma'] else 'ldg'}{'dense' if c.get('dense') else ''}{('m%d' % c['group']) if c.get('kernel') == 1 else ''}")
+@pytest.mark.parametrize("cfg", CONFIGS, ids=lambda c: f"S{c['cluster']}T{c['threads']}{'tma' if c['use_tma'] else 'ldg'}{('pack' if c.get('dense') == 2 else 'dense') if c.get('dense') else ''}{('m%d' % c['group']) if c.get('kernel') == 1 else ''}")
 def test_closed_loop_vs_reference_channel(golden, name, cfg, trk_mode):
     from oracle import sydr_oracle as O
     if cfg.get("kernel") == 1 and (name != "fs25" or trk_mode != 0):

@@ -61,6 +61,8 @@ trk = pipe._trk
 for _ in range(3):
     t0 = time.perf_counter()
     trk._nep_host.copy_(trk._nep, non_blocking=True)
+    trk._out_host = trk._out_ring[0] if trk._out_ring[0] is not None else torch.empty(trk.n_ch * trk.max_epochs * 128, dtype=torch.uint8, pin_memory=True)
+    trk._out_ring[0] = trk._out_host
     trk._out_host.copy_(trk._out, non_blocking=True)
     t1 = time.perf_counter()
     torch.cuda.current_stream().synchronize()
