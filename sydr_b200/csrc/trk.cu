@@ -20,6 +20,8 @@
 // sums are all-gathered with st.async (DSMEM store + remote mbarrier complete_tx), after which
 // every CTA closes the loops redundantly in FP64 (bit-identical), so one exchange per epoch
 // is the only inter-CTA synchronisation.
+#include <cstdlib>
+#include <cstdio>
 #include "trk_common.cuh"
 
 namespace sydr {
@@ -495,6 +497,10 @@ int launch_trk(const TrkParams& P, int n_channels, int cluster, int threads, int
         }
     }
     SYDR_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_launch));
+    static const bool trace = getenv("SYDR_TRK_TRACE") != nullptr;      // diagnostics: the shape of every tracking launch
+    if (trace)
+        fprintf(stderr, "[sydr] trk launch: %d channels, cluster %d, %d threads, %s, %zu B dynamic smem\n", n_channels, cluster, threads,
+                lean ? "LEAN" : (P.dense == 2 ? "PACK" : (P.kstates ? "KAP" : (P.dense ? "DENSE" : "latency"))), smem_launch);
     cudaLaunchConfig_t lc = {};
     lc.gridDim = dim3((unsigned)(n_channels * cluster));
     lc.blockDim = dim3((unsigned)threads);
@@ -653,9 +659,21 @@ static int trk_run_impl(const void* d_iq, int iq_dtype, long long iq_alloc_sampl
     // B200 (profiles/r2/pack_shapes.txt), SM time per channel-epoch: staged kernel, one CTA of 384 threads per SM 3.75 us
     // (<= 148 channels); PACK, two CTAs per SM 3.1 us (<= 296 channels); LEAN, three CTAs per SM 4.0 us (beyond).
     bool staged_one = false;
-    if (auto_shape && staged_ok && !(cfg && cfg->kernel == 1) && threads <= 0) {
+    const bool auto_throughput = auto_shape && staged_ok && !(cfg && cfg->kernel == 1) && threads <= 0;
+    if (auto_throughput && n_channels > kPackWave && win1 <= kPackWindowBytes) {
+        // more channels than one wave of the PACK shape holds: waves of 296 channels, one launch each on the same stream (a wave
+        // of the LEAN shape holds 444 channels but takes twice as long), the remainder in the shape that fits it
+        for (int c0 = 0; c0 < n_channels; c0 += kPackWave) {
+            const int nc = (n_channels - c0 < kPackWave) ? n_channels - c0 : kPackWave;
+            rc = trk_run_impl(d_iq, iq_dtype, iq_alloc_samples, fs, d_states + c0, nc, d_out + (size_t)c0 * max_epochs, max_epochs,
+                              d_nepochs + c0, cfg, stream, nullptr, nullptr);
+            if (rc != SYDR_OK) return rc;
+        }
+        return SYDR_OK;
+    }
+    if (auto_throughput) {
         if (n_channels <= 148 && 2 * win1 <= 200 * 1024) staged_one = true;
-        else if (n_channels <= 296 && win1 <= kPackWindowBytes) pack = true;
+        else if (n_channels <= kPackWave && win1 <= kPackWindowBytes) pack = true;
     }
     if (pack && threads <= 0) threads = kPackThreads;
     if (staged_one) threads = kTrkMaxThreads;

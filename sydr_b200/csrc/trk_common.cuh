@@ -788,6 +788,7 @@ constexpr int kTrkMaxThreads = 384;
 constexpr int kDenseMaxThreads = 288;    // DENSE instantiation: <= 113 registers, three CTAs per SM beside other launches
 constexpr int kLeanThreads = 256;
 constexpr int kPackThreads = 320;        // PACK instantiation: two CTAs per SM under 102 registers
+constexpr int kPackWave = 296;           // channels one launch of the PACK shape holds (two per SM)
 constexpr int kPackWindowBytes = 108 * 1024;   // its single window: what two CTAs per SM leave of 227 KB beside 5 KB of static shared memory
 constexpr int kKaplanMaxThreads = 384;   // the Kaplan carrier warp holds more state: 170 registers per thread instead of 102
 constexpr int kNeedGeneral = 2;  // channel status: stopped in front of an epoch only the general kernel serves

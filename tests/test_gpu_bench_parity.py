@@ -188,6 +188,44 @@ def test_batch_step_vs_pipeline_and_oracle():
     print("batch step vs oracle:", {k: max(r[k] for r in res) for k in ("e_corr", "e_state", "d_car", "d_code", "d_phase")})
 
 
+def test_more_channels_than_a_wave():
+    """Automatic shape beyond 296 channels: waves of the PACK shape (296 channels per launch), the remainder in its own
+    launch (here 4 channels: clusters of 8).  25 copies of the 12 channels of one recording + the 12 tracked alone: every
+    copy inside a wave equals the first bit for bit, all of them follow the lone run within the loop tolerances."""
+    import torch
+    from sydr_b200 import synth
+    from sydr_b200.engine import AcquisitionEngine, TrackingEngine, make_trk_states
+    seconds = 0.25
+    n = int(round(seconds * FS))
+    sc = synth.make_scenario(FS, 16, seconds, synth.PRNS_12, 1201, 250.0)
+    buf = torch.zeros(2 * n + 4096, dtype=torch.int16, device="cuda")
+    buf[:2 * n] = synth.generate_iq_torch(sc, device="cuda")
+    acq = AcquisitionEngine(FS, 0.0, 5000.0, 250.0, 1, 10, list(synth.PRNS_12))
+    chans = []
+    for p in acq.run(buf[:2 * n])["peaks"]:
+        carrier, _, cur = acq.handoff(p)
+        chans.append(dict(prn=int(p["prn"]), carrier_freq=carrier, start_sample=cur, iq_len=n))
+    acq.close()
+    assert len(chans) == 12
+    many = chans * 25                                        # 300 channels: one wave of 296 + 4
+    eng = TrackingEngine(FS, make_trk_states(FS, many), int(seconds * 1000) + 8)
+    eng.launch(buf[:2 * n])
+    recs = eng.fetch()
+    assert (eng.states()["status"] == 0).all() and min(len(r) for r in recs) >= 235
+    lone = TrackingEngine(FS, make_trk_states(FS, chans), int(seconds * 1000) + 8)
+    lone.launch(buf[:2 * n])
+    ref = lone.fetch()
+    for i, r in enumerate(recs):
+        if 12 <= i < 296:
+            assert r.tobytes() == recs[i % 12].tobytes()
+        e = ref[i % 12]
+        m = min(len(r), len(e))
+        assert abs(len(r) - len(e)) <= 1
+        assert np.abs(r["carrier_freq"][:m] - e["carrier_freq"][:m]).max() <= TOL_HZ
+        assert np.abs(r["code_freq"][:m] - e["code_freq"][:m]).max() <= TOL_HZ
+        assert np.abs(r["start"][:m] - e["start"][:m]).max() <= 1
+
+
 @pytest.mark.parametrize("shape", list(SHAPES))
 def test_throughput_instantiation_vs_oracle(shape):
     """configs[4] shape: 3 recordings x 12 channels x 0.5 s in one launch of the throughput kernels: the
