@@ -243,7 +243,6 @@ def fill_batch(batch, sc0, host, rank, args, dev):
     from sydr_b200 import synth
     B, S = batch.B, max(1, min(args.seeds, batch.B))
     scs = [None] * B
-    dwell = 2 * batch.acq.required_samples
     j = 0
     for i in range(S):
         if i == 0:
@@ -254,7 +253,7 @@ def fill_batch(batch, sc0, host, rank, args, dev):
                 j += 1
                 sc = synth.make_scenario(FS, NBITS, args.chunk_seconds, synth.PRNS_12, 2003 + 16 * j + rank, 250.0)
                 batch.slot(i).copy_(synth.generate_iq_torch(sc, device=dev))
-                pk = batch.acq.run(batch.slot(i)[:dwell])["peaks"]
+                pk = batch.acq.run(batch.slot(i)[:2 * batch.acq.required_samples])["peaks"]
                 if sorted(int(p["prn"]) for p in pk if p["ratio"] > batch.threshold) == sorted(s_.prn for s_ in sc.sats):
                     break
                 if j > 4 * S + 8:

@@ -2,6 +2,7 @@
 config keys as the GPU arm, `impl`, `cpu_baseline` with kind / cores / sample, an `e2e` object with zero copy bytes), the
 tracked DRAM-traffic file the GPU arm reads, and the legacy prototype table against the header."""
 import json
+import numpy as np
 import os
 import re
 import subprocess
@@ -35,6 +36,35 @@ def test_tracked_traffic_file():
     assert all(os.path.exists(os.path.join(H.ROOT, src)) for src in info["sources"])
     # the tracking launch of a step reads the samples of its 24 recordings once: 24 x 4 B x 25 MS/s x 60 s, plus the records
     assert 0.98 * 24 * 6.0e9 < info["trk_borre_kernel"] < 1.1 * 24 * 6.0e9 and total > info["trk_borre_kernel"]
+
+
+def test_batch_slots_hold_different_samples():
+    """bench.fill_batch: the slots beyond the generated recordings are those times j, -1, -j (CPU stand-in for the batch)."""
+    import types
+    import torch
+    sys.path.insert(0, H.ROOT)
+    import bench
+    n = 64
+    store = torch.zeros(4 * 2 * n, dtype=torch.int16)
+
+    class FakeBatch:
+        B = 4
+
+        def slot(self, r):
+            return store[r * 2 * n:(r + 1) * 2 * n]
+
+    real_sync = torch.cuda.synchronize
+    torch.cuda.synchronize = lambda *a, **k: None
+    try:
+        host = torch.randint(-3000, 3000, (2 * n,), dtype=torch.int16)
+        scs = bench.fill_batch(FakeBatch(), "sc0", host, 0, types.SimpleNamespace(seeds=1, chunk_seconds=0.0), "cpu")
+    finally:
+        torch.cuda.synchronize = real_sync
+    assert scs == ["sc0"] * 4
+    x = host.numpy().astype(np.float64).view(np.complex128)
+    for r, f in enumerate((1, 1j, -1, -1j)):
+        got = store[r * 2 * n:(r + 1) * 2 * n].numpy().astype(np.float64).view(np.complex128)
+        assert np.array_equal(got, f * x), r
 
 
 def test_legacy_prototypes_cover_the_header():
