@@ -614,6 +614,7 @@ def main():
     ap.add_argument("--recordings", type=int, default=24,
                     help="recordings per step and GPU, tracked by one launch (ColdStartBatch): 24 x 12 channels = two CTAs on each of 144 SMs")
     ap.add_argument("--seeds", type=int, default=6, help="recordings of a batch that are generated; the others are these times j, -1, -j")
+    ap.add_argument("--e2e-steps", type=int, default=0, help="end-to-end leg: steps (of --recordings recordings each) timed; 0 = steps / 10")
     ap.add_argument("--lanes", type=int, default=5, help="end-to-end leg: recordings in flight per GPU (ColdStartPool)")
     ap.add_argument("--cluster", type=int, default=0)
     ap.add_argument("--threads", type=int, default=0)
@@ -684,7 +685,7 @@ def main():
                          max_seconds=args.chunk_seconds, device=dev, cluster=args.cluster, threads=args.threads,
                          use_tma=not args.no_tma, **ACQ)
     pipe = pool.lanes[0]
-    e2e_hist = torch.zeros(max(args.steps, 2) * PEAK_BYTES, dtype=torch.uint8, device=dev) if world > 1 else None
+    e2e_hist = torch.zeros(64 * PEAK_BYTES, dtype=torch.uint8, device=dev) if world > 1 else None
 
     def e2e_slot():
         if world == 1 or args.no_gather:
@@ -718,16 +719,18 @@ def main():
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()                                 # (NVML start-up takes milliseconds: before the barrier); rank 0's GPU only
+    # an end-to-end step is the device-resident step's batch: B recordings (B x 6 GB up, B x 92 MB of records down); the leg is
+    # PCIe-bound and in steady state after a few recordings, so it times --e2e-steps (default K / 10) such steps
+    e2e_steps = args.e2e_steps if args.e2e_steps > 0 else max(1, args.steps // 10)
     run_pool_steps(2)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    run_pool_steps(args.steps)
+    run_pool_steps(e2e_steps * B)
     barrier()
     e1.record()
     torch.cuda.synchronize()
     ms_e2e = e0.elapsed_time(e1)
-    e2e_steps = args.steps
     pool.close()
     for p_ in pool.lanes:
         p_._d_iq_buf = None
@@ -887,7 +890,7 @@ def main():
     per_rank_ms = [round(float(v), 3) for v in per_rank.cpu()]
     total_samples = float(chunk_samples) * B * world * args.steps
     value = total_samples / (ms_dev * 1e-3) / 1e6
-    e2e = float(chunk_samples) * world * e2e_steps / (ms_e2e * 1e-3) / 1e6
+    e2e = float(chunk_samples) * B * world * e2e_steps / (ms_e2e * 1e-3) / 1e6
 
     if rank == 0:
         peaks_file = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -963,8 +966,11 @@ def main():
                             "latency shape (acquisition, hand-off, then its serial chain of tracking epochs; first launch to last, CUDA events)",
                 "config": workload_config(args, world), "clocks": clocks,
                 "e2e": {"value": e2e, "unit": "Msamples/s", "rtf": e2e * 1e6 / FS / world,
-                        "h2d_bytes_per_step": int(host.numel() * host.element_size()), "d2h_bytes_per_step": int(d2h_bytes),
-                        "steps": e2e_steps, "step": "one recording (6 GB up, all epoch records down)", "recordings_in_flight": args.lanes,
+                        "h2d_bytes_per_step": int(host.numel() * host.element_size()) * B, "d2h_bytes_per_step": int(d2h_bytes) * B,
+                        "steps": e2e_steps, "ms_per_step": ms_e2e / e2e_steps,
+                        "step": f"{B} recordings, one submit_host / result pair each ({host.numel() * host.element_size() / 1e9:.1f} GB up, the peak table and "
+                                "all epoch records down per recording); the uploads of a step read the same pinned host recording",
+                        "recordings_in_flight": args.lanes,
                         "call": "ColdStartPool.submit_host(pinned int16 IQ) / result(): H2D in 4 pieces on a copy stream, acquisition, device "
                                 "hand-off, tracking behind the upload (latency shape), D2H of the peak table and of all epoch records into a "
                                 "ring of pinned result buffers (returned as views)"},
