@@ -232,7 +232,11 @@ class ColdStartPool:
     independent ColdStartPipeline instances, each on its own stream; submit_*() enqueues a whole
     step on the next lane and returns a ticket at once, result() hands back what process_*() would.
     With two lanes the step period drops from acquisition + tracking to about the SM-time bound
-    (5.7 -> 4.4 ms for the headline chunk)."""
+    (5.7 -> 4.4 ms for the headline chunk).  This is the shape for recordings that ARRIVE one by one (submit_host: the
+    upload of one overlaps the tracking of another; PCIe-bound).  Recordings already resident in HBM are tracked
+    2.1 x faster side by side in one launch (ColdStartBatch); with more than 2 lanes x 3 streams set
+    CUDA_DEVICE_MAX_CONNECTIONS=32 before CUDA starts, or streams share hardware queues and serialise
+    (profiles/r2/pack_shapes.txt)."""
 
     def __init__(self, lanes: int = 2, **pipeline_kwargs):
         pipeline_kwargs.setdefault("dense", int(lanes) > 1)       # launches share the GPU: pack the tracking CTAs 3 per SM
